@@ -1,0 +1,80 @@
+"""Generate golden vectors from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py          # needs /root/reference
+
+The reference (aharley/pips, nets/pips.py) is imported as-is; the only shim is
+``torch.Tensor.cuda = identity`` because nets/pips.py:429 calls ``.cuda()`` on a
+scalar that is never used.  Weights come from
+``oracle.pips_oracle.init_state_dict`` and are loaded with ``strict=True``, which
+also pins the state_dict key/shape contract of SURVEY.md section 8b.  Inputs are
+regenerated from seeds by the tests, so only outputs are stored.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from oracle import pips_oracle as po  # noqa: E402
+
+CASES = {
+    # name: dict(B, H, W, N, stride, iters, head_scale, seed, oob, warm)
+    "tiny_s8": dict(B=1, H=128, W=128, N=12, stride=8, iters=3, head_scale=0.05, seed=1, oob=False, warm=False),
+    "rect_s4_oob": dict(B=2, H=128, W=192, N=20, stride=4, iters=6, head_scale=0.05, seed=2, oob=True, warm=False),
+    "odd_s8": dict(B=1, H=184, W=360, N=16, stride=8, iters=4, head_scale=0.02, seed=3, oob=True, warm=False),
+    "warm_s8": dict(B=1, H=128, W=160, N=10, stride=8, iters=2, head_scale=0.05, seed=4, oob=False, warm=True),
+    "undamped_1it": dict(B=1, H=128, W=128, N=8, stride=8, iters=1, head_scale=1.0, seed=5, oob=False, warm=False),
+}
+
+
+def case_inputs(c):
+    """Shared with tests/: deterministic inputs for a golden case."""
+    rgbs = po.smooth_video(c["B"], 8, c["H"], c["W"], seed=100 + c["seed"])
+    xys = po.random_queries(c["B"], c["N"], c["H"], c["W"], seed=200 + c["seed"])
+    if c["oob"]:
+        # push a few queries onto / across the border: exercises zero padding in the
+        # correlation sampler and index clamping in the initial feature gather
+        xys[:, 0] = torch.tensor([0.0, 0.0])
+        xys[:, 1] = torch.tensor([c["W"] - 1.0, c["H"] - 1.0])
+        xys[:, 2] = torch.tensor([-5.5, 17.25])
+        xys[:, 3] = torch.tensor([c["W"] + 3.0, c["H"] + 6.5])
+        xys[:, 4] = torch.tensor([float(c["stride"] * 5), float(c["stride"] * 7)])   # exact integer grid coords
+    extra = {}
+    if c["warm"]:
+        g = torch.Generator().manual_seed(300 + c["seed"])
+        drift = torch.cumsum(torch.randn(c["B"], 8, c["N"], 2, generator=g) * 1.5, 1)
+        extra["coords_init"] = xys[:, None] + drift - drift[:, :1]
+        extra["feat_init"] = torch.randn(c["B"], c["N"], 128, generator=g) * 0.5
+    return rgbs, xys, extra
+
+
+def main():
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    from nets.pips import Pips  # the reference, unmodified
+
+    torch.set_num_threads(8)
+    out = {}
+    for name, c in CASES.items():
+        sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+        model = Pips(S=8, stride=c["stride"]).eval()
+        model.load_state_dict(sd, strict=True)
+        rgbs, xys, extra = case_inputs(c)
+        with torch.no_grad():
+            preds, preds2, vis_e, ffeat, losses = model(xys, rgbs, iters=c["iters"], return_feat=True, **extra)
+        assert losses is None and len(preds2) == c["iters"] + 4
+        out[name + "/preds"] = torch.stack(preds).numpy()
+        out[name + "/vis_e"] = vis_e.numpy()
+        out[name + "/ffeat"] = ffeat.numpy()
+        print(name, "trajs_e range", float(preds[-1].min()), float(preds[-1].max()),
+              "mean |d| from init", float((preds[-1] - xys[:, None]).abs().mean()))
+    np.savez_compressed(os.path.join(HERE, "reference_outputs.npz"), **out)
+    print("wrote", os.path.join(HERE, "reference_outputs.npz"))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,64 @@
+"""Pins oracle/pips_oracle.py against outputs of the unmodified reference
+(tests/golden/reference_outputs.npz, written by tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pips_oracle as po
+from tests.golden.make_golden import CASES, case_inputs
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.npz"))
+
+# fp32 re-association noise of the reference against itself (1 vs 8 threads) on the
+# damped fixtures is <= 2e-4 px after 6 iterations.
+TOL_PX = 1e-3
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("allpairs", [True, False])
+def test_oracle_matches_reference(name, allpairs):
+    c = CASES[name]
+    sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+    rgbs, xys, extra = case_inputs(c)
+    with torch.no_grad():
+        preds, preds2, vis_e, ffeat, losses = po.forward(
+            sd, xys, rgbs, iters=c["iters"], stride=c["stride"], allpairs=allpairs, return_feat=True, **extra)
+    assert losses is None
+    assert len(preds) == c["iters"] and len(preds2) == c["iters"] + 4
+    got = torch.stack(preds).numpy()
+    ref = GOLD[name + "/preds"]
+    assert got.shape == ref.shape
+    tol = TOL_PX if c["head_scale"] < 1.0 else 5e-3
+    assert np.abs(got - ref).max() < tol, np.abs(got - ref).max()
+    assert np.abs(ffeat.numpy() - GOLD[name + "/ffeat"]).max() < 1e-5
+    assert np.abs(vis_e.numpy() - GOLD[name + "/vis_e"]).max() < 2e-3
+    # anim list layout, nets/pips.py:474-475, :562-563
+    assert torch.equal(preds2[0], preds2[1]) and torch.equal(preds2[-1], preds2[-2]) and torch.equal(preds2[-1], preds[-1])
+
+
+def test_state_dict_spec_counts():
+    spec = po.state_dict_spec()
+    assert len(spec) == 200
+    total = sum(int(np.prod(s)) for _, s in spec)
+    assert total == 28677713
+
+
+def test_corr_local_equals_allpairs():
+    torch.manual_seed(0)
+    B, S, N, C, H, W = 2, 8, 9, 128, 20, 28
+    fmaps = torch.randn(B, S, C, H, W)
+    pyr = po.build_pyramid(fmaps)
+    coords = torch.rand(B, S, N, 2) * torch.tensor([W + 8.0, H + 8.0]) - 4.0
+    coords[0, 0, 0] = torch.tensor([3.0, 5.0])
+    tg = torch.randn(B, S, N, C)
+    a = po.sample_allpairs(po.corr_allpairs(pyr, tg), coords)
+    b = po.corr_local(pyr, tg, coords)
+    assert a.shape == (B, S, N, 196)
+    assert (a - b).abs().max() < 2e-4
+
+
+def test_times_axis_is_linspace_0_S():
+    t = po.times_axis(8)
+    assert t[0] == 0 and t[-1] == 8 and abs(float(t[1]) - 8 / 7) < 1e-6

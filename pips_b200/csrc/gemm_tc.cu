@@ -1,0 +1,335 @@
+// Mixer dense layers on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+//   C[M,N] = epilogue( A[M,K] . W[N,K]^T + bias[N] )
+//
+// A (activations) and W (nn.Linear weight, (out,in) == N x K, K-major) are bf16.  In the
+// "bf16x3" precision mode both operands are carried as a (hi, lo) bf16 pair with
+// v ~= hi + lo, and the product is evaluated as A_hi.W_hi + A_lo.W_hi + A_hi.W_lo with fp32
+// accumulation in TMEM (relative error ~2^-16 per product instead of 2^-8), which is what the
+// 1e-3 px parity target of the refinement loop needs (reference: fp32 nn.Linear,
+// nets/pips.py:104-107,:115,:122).
+//
+// Structure (one CTA per SM, persistent over 128x256 output tiles):
+//   warp 0      TMA producer   : cp.async.bulk.tensor 128B-swizzled K-chunks of A and W -> smem ring
+//   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (M=128,N=256,K=16) per chunk/term
+//   warp 2      TMEM allocator
+//   warps 4..7  epilogue       : tcgen05.ld the fp32 tile (one row per thread), bias / GELU(erf) /
+//                                residual / hi-lo split, vectorised stores
+// The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i
+// overlaps the MMAs of tile i+1.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace pips {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;                       // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr uint32_t A_TILE_BYTES = BM * BK * 2;     // 16 KB
+constexpr uint32_t W_TILE_BYTES = BN * BK * 2;     // 32 KB
+
+template <int TERMS>
+struct GemmCfg {
+    static constexpr int kOperandCopies = TERMS == 3 ? 2 : 1;             // hi (+ lo)
+    static constexpr uint32_t kStageBytes = kOperandCopies * (A_TILE_BYTES + W_TILE_BYTES);
+    static constexpr int kStages = TERMS == 3 ? 2 : 4;
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmArgs {
+    int M, N, K;                 // valid rows / cols, K multiple of 64
+    const float* bias;           // [N]
+    int epilogue;                // PIPS_EPI_*
+    float* out_f32;              // BIAS / BIAS_RESID target (row stride ldo)
+    int ldo;
+    __nv_bfloat16* out_hi;       // BIAS_GELU target (row stride ldh); out_lo may be null
+    __nv_bfloat16* out_lo;
+    int ldh;
+};
+
+template <int TERMS>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+               const GemmArgs args) {
+    using Cfg = GemmCfg<TERMS>;
+    constexpr int kStages = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    // 128B swizzle atoms need 1024-byte alignment
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    // barrier layout: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
+    const uint32_t full0 = smem_u32(bars);
+    const uint32_t empty0 = full0 + 8 * kStages;
+    const uint32_t tfull0 = empty0 + 8 * kStages;
+    const uint32_t tempty0 = tfull0 + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int tiles_m = (args.M + BM - 1) / BM;
+    const int tiles_n = (args.N + BN - 1) / BN;
+    const int num_tiles = tiles_m * tiles_n;
+    const int num_kb = args.K / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi);
+        tma_prefetch_desc(&map_w_hi);
+        if (TERMS == 3) {
+            tma_prefetch_desc(&map_a_lo);
+            tma_prefetch_desc(&map_w_lo);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull0 + 8 * s, 1);
+            mbar_init(tempty0 + 8 * s, 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_slot), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m0 = (t / tiles_n) * BM;
+                const int n0 = (t % tiles_n) * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t fb = full0 + 8 * stage;
+                    mbar_arrive_expect_tx(fb, Cfg::kStageBytes);
+                    const uint32_t base = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const int k0 = kb * BK;
+                    tma_load_2d(base, &map_a_hi, fb, k0, m0);
+                    tma_load_2d(base + A_TILE_BYTES, &map_w_hi, fb, k0, n0);
+                    if (TERMS == 3) {
+                        tma_load_2d(base + A_TILE_BYTES + W_TILE_BYTES, &map_a_lo, fb, k0, m0);
+                        tma_load_2d(base + 2 * A_TILE_BYTES + W_TILE_BYTES, &map_w_lo, fb, k0, n0);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            uint32_t stage = 0, phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                mbar_wait(tempty0 + 8 * as, aphase ^ 1);      // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t base = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint64_t a_hi = umma_desc_sw128(base);
+                    const uint64_t w_hi = umma_desc_sw128(base + A_TILE_BYTES);
+                    const uint64_t a_lo = umma_desc_sw128(base + A_TILE_BYTES + W_TILE_BYTES);
+                    const uint64_t w_lo = umma_desc_sw128(base + 2 * A_TILE_BYTES + W_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adv = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);   // 32 B per K=16 step
+                        umma_f16(d_tmem, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+                        if (TERMS == 3) {
+                            umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
+                            umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                        }
+                    }
+                    umma_commit(empty0 + 8 * stage);          // smem slot reusable once these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(tfull0 + 8 * as);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------ epilogue (128 threads, one row each)
+        const int q = warp - 4;                                  // == warp % 4: TMEM lane quadrant
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+            const int m0 = (t / tiles_n) * BM;
+            const int n0 = (t % tiles_n) * BN;
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < args.M;
+            mbar_wait(tfull0 + 8 * as, aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + c0, v);
+                tmem_ld_wait();
+                const int col = n0 + c0;
+                if (col >= args.N) continue;                     // warp-uniform
+                const bool full_chunk = col + 32 <= args.N;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 b;
+                    if (full_chunk) {
+                        b = __ldg(reinterpret_cast<const float4*>(args.bias + col + j));
+                    } else {
+                        b.x = col + j + 0 < args.N ? __ldg(args.bias + col + j + 0) : 0.f;
+                        b.y = col + j + 1 < args.N ? __ldg(args.bias + col + j + 1) : 0.f;
+                        b.z = col + j + 2 < args.N ? __ldg(args.bias + col + j + 2) : 0.f;
+                        b.w = col + j + 3 < args.N ? __ldg(args.bias + col + j + 3) : 0.f;
+                    }
+                    f[j + 0] = __uint_as_float(v[j + 0]) + b.x;
+                    f[j + 1] = __uint_as_float(v[j + 1]) + b.y;
+                    f[j + 2] = __uint_as_float(v[j + 2]) + b.z;
+                    f[j + 3] = __uint_as_float(v[j + 3]) + b.w;
+                }
+                if (row_ok && args.epilogue == PIPS_EPI_BIAS_GELU) {
+                    __nv_bfloat16* ph = args.out_hi + static_cast<size_t>(row) * args.ldh + col;
+                    __nv_bfloat16* pl = args.out_lo ? args.out_lo + static_cast<size_t>(row) * args.ldh + col : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint32_t hw[4], lw[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float g0 = gelu_exact(f[j + 2 * e]);
+                            const float g1 = gelu_exact(f[j + 2 * e + 1]);
+                            const __nv_bfloat16 h0 = __float2bfloat16_rn(g0), h1 = __float2bfloat16_rn(g1);
+                            hw[e] = pack_bf16(h0, h1);
+                            lw[e] = pack_bf16(__float2bfloat16_rn(g0 - __bfloat162float(h0)),
+                                              __float2bfloat16_rn(g1 - __bfloat162float(h1)));
+                        }
+                        if (full_chunk) {
+                            *reinterpret_cast<uint4*>(ph + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                            if (pl) *reinterpret_cast<uint4*>(pl + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                        } else {
+                            for (int e = 0; e < 8; ++e) {
+                                if (col + j + e < args.N) {
+                                    const uint32_t hh = hw[e >> 1], ll = lw[e >> 1];
+                                    reinterpret_cast<uint16_t*>(ph)[j + e] = (e & 1) ? (hh >> 16) : (hh & 0xffff);
+                                    if (pl) reinterpret_cast<uint16_t*>(pl)[j + e] = (e & 1) ? (ll >> 16) : (ll & 0xffff);
+                                }
+                            }
+                        }
+                    }
+                } else if (row_ok) {
+                    float* po = args.out_f32 + static_cast<size_t>(row) * args.ldo + col;
+                    const bool resid = args.epilogue == PIPS_EPI_BIAS_RESID;
+                    if (full_chunk) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 o = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                            if (resid) {
+                                const float4 r = *reinterpret_cast<const float4*>(po + j);
+                                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                            }
+                            *reinterpret_cast<float4*>(po + j) = o;
+                        }
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (col + j < args.N) po[j] = resid ? po[j] + f[j] : f[j];
+                    }
+                }
+                __syncwarp();                                    // tcgen05.ld is warp-collective: reconverge
+            }
+            tc_fence_before();
+            mbar_arrive(tempty0 + 8 * as);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------- host side
+
+static bool make_operand_map(CUtensorMap* map, const void* ptr, int rows, int K, int ld_elems, int box_rows) {
+    // global tensor (innermost first): {K, rows}, row stride ld_elems*2 bytes; box {64, box_rows}, 128B swizzle
+    cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+    cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld_elems) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    return encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace pips
+
+using namespace pips;
+
+extern "C" int pips_gemm_tc(const void* a_hi, const void* a_lo, int lda, int a_rows,
+                            const void* w_hi, const void* w_lo, int ldw, int w_rows,
+                            int M, int N, int K, const float* bias, int epilogue,
+                            float* out_f32, int ldo, void* out_hi, void* out_lo, int ldh,
+                            void* stream) {
+    if (K % BK != 0 || K <= 0) return fail("pips_gemm_tc: K must be a positive multiple of 64");
+    if (M <= 0 || N <= 0) return fail("pips_gemm_tc: empty problem");
+    if (a_rows < M || w_rows < N) return fail("pips_gemm_tc: operand allocations smaller than the problem");
+    if ((lda % 8) || (ldw % 8)) return fail("pips_gemm_tc: leading dimensions must be multiples of 8 elements (16 B)");
+    if (!bias) return fail("pips_gemm_tc: bias is required");
+    const bool x3 = a_lo != nullptr && w_lo != nullptr;
+    if ((a_lo != nullptr) != (w_lo != nullptr)) return fail("pips_gemm_tc: need both or neither lo operands");
+    if (epilogue == PIPS_EPI_BIAS_GELU) {
+        if (!out_hi || (ldh % 8)) return fail("pips_gemm_tc: GELU epilogue needs out_hi with ldh % 8 == 0");
+    } else if (epilogue == PIPS_EPI_BIAS || epilogue == PIPS_EPI_BIAS_RESID) {
+        if (!out_f32 || (ldo % 4)) return fail("pips_gemm_tc: fp32 epilogue needs out_f32 with ldo % 4 == 0");
+    } else {
+        return fail("pips_gemm_tc: unknown epilogue");
+    }
+    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+    if (!make_operand_map(&ma_hi, a_hi, a_rows, K, lda, BM)) return fail("pips_gemm_tc: tensor map (A hi) failed");
+    if (!make_operand_map(&mw_hi, w_hi, w_rows, K, ldw, BN)) return fail("pips_gemm_tc: tensor map (W hi) failed");
+    ma_lo = ma_hi;
+    mw_lo = mw_hi;
+    if (x3) {
+        if (!make_operand_map(&ma_lo, a_lo, a_rows, K, lda, BM)) return fail("pips_gemm_tc: tensor map (A lo) failed");
+        if (!make_operand_map(&mw_lo, w_lo, w_rows, K, ldw, BN)) return fail("pips_gemm_tc: tensor map (W lo) failed");
+    }
+    GemmArgs args;
+    args.M = M; args.N = N; args.K = K; args.bias = bias; args.epilogue = epilogue;
+    args.out_f32 = out_f32; args.ldo = ldo;
+    args.out_hi = static_cast<__nv_bfloat16*>(out_hi); args.out_lo = static_cast<__nv_bfloat16*>(out_lo); args.ldh = ldh;
+    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    if (x3) {
+        static bool attr = false;
+        if (!attr) {
+            e = cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<3>::kSmemBytes);
+            if (e != cudaSuccess) return fail_cuda("pips_gemm_tc: smem attribute", e);
+            attr = true;
+        }
+        gemm_tc_kernel<3><<<grid, GEMM_THREADS, GemmCfg<3>::kSmemBytes, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, args);
+    } else {
+        static bool attr = false;
+        if (!attr) {
+            e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::kSmemBytes);
+            if (e != cudaSuccess) return fail_cuda("pips_gemm_tc: smem attribute", e);
+            attr = true;
+        }
+        gemm_tc_kernel<1><<<grid, GEMM_THREADS, GemmCfg<1>::kSmemBytes, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, args);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda("pips_gemm_tc: launch", e);
+    return 0;
+}

@@ -1,0 +1,254 @@
+"""Host driver of the CUDA refinement loop: weight packing, persistent buffers, launches.
+
+Everything numerical happens in libpips_b200.so (include/pips_b200.h); torch is used for device
+memory and streams only.  The driver mirrors the state machine of ``Pips.forward`` in the reference
+(nets/pips.py:450-559): coords / ffeats state, one ``pips_refine_iter`` per iteration, vis head.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+S_FRAMES = 8
+LATENT = 128
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+class PackedWeights:
+    """Kernel-layout copies of the DeltaBlock / head parameters.
+
+    Dense-layer weights are kept as nn.Linear stores them ((out, in) == N x K, K-major), split into a
+    bf16 (hi, lo) pair for the tcgen05 path; the first Linear's K is zero-padded 519 -> 576 and the
+    last Linear's N 1040 -> 1280 so that TMA boxes never leave the allocation.
+    """
+
+    def __init__(self, module, stream):
+        lib = L.load()
+        sd = {k: v.detach() for k, v in module.state_dict().items()}
+        dev = sd["norm.weight"].device
+        if dev.type != "cuda":
+            raise L.PipsCudaError("pips_b200: the refinement path needs the module on a CUDA device")
+        self.device = dev
+        self.keep = []                       # tensors referenced by raw pointer from the struct
+        self.c = L.Weights()
+
+        def f32(t):
+            t = t.to(torch.float32).contiguous()
+            self.keep.append(t)
+            return t
+
+        def split(t):
+            t = f32(t)
+            hi = torch.empty(t.shape, dtype=torch.bfloat16, device=dev)
+            lo = torch.empty(t.shape, dtype=torch.bfloat16, device=dev)
+            L.check(lib.pips_split_bf16(L.ptr(t), L.ptr(hi), L.ptr(lo), t.numel(), stream), "pips_split_bf16")
+            self.keep += [hi, lo]
+            return hi, lo, t
+
+        td = "delta_block.to_delta"
+        w0 = torch.zeros(L.DIM, L.KPAD, dtype=torch.float32, device=dev)
+        w0[:, :519] = sd[f"{td}.0.weight"]
+        hi, lo, f = split(w0)
+        self.c.in_w_hi, self.c.in_w_lo, self.c.in_w_f32 = L.ptr(hi), L.ptr(lo), L.ptr(f)
+        self.c.in_b = L.ptr(f32(sd[f"{td}.0.bias"]))
+        for l in range(L.DEPTH):
+            p = f"{td}.{l + 1}"
+            lw = self.c.layer[l]
+            lw.ln1_w, lw.ln1_b = L.ptr(f32(sd[p + ".0.norm.weight"])), L.ptr(f32(sd[p + ".0.norm.bias"]))
+            lw.tok_w1 = L.ptr(f32(sd[p + ".0.fn.0.weight"].reshape(4 * S_FRAMES, S_FRAMES)))
+            lw.tok_b1 = L.ptr(f32(sd[p + ".0.fn.0.bias"]))
+            lw.tok_w2 = L.ptr(f32(sd[p + ".0.fn.3.weight"].reshape(S_FRAMES, 4 * S_FRAMES)))
+            lw.tok_b2 = L.ptr(f32(sd[p + ".0.fn.3.bias"]))
+            lw.ln2_w, lw.ln2_b = L.ptr(f32(sd[p + ".1.norm.weight"])), L.ptr(f32(sd[p + ".1.norm.bias"]))
+            hi, lo, f = split(sd[p + ".1.fn.0.weight"])
+            lw.fc1_w_hi, lw.fc1_w_lo, lw.fc1_w_f32 = L.ptr(hi), L.ptr(lo), L.ptr(f)
+            lw.fc1_b = L.ptr(f32(sd[p + ".1.fn.0.bias"]))
+            hi, lo, f = split(sd[p + ".1.fn.3.weight"])
+            lw.fc2_w_hi, lw.fc2_w_lo, lw.fc2_w_f32 = L.ptr(hi), L.ptr(lo), L.ptr(f)
+            lw.fc2_b = L.ptr(f32(sd[p + ".1.fn.3.bias"]))
+        self.c.out_ln_w, self.c.out_ln_b = L.ptr(f32(sd[f"{td}.13.weight"])), L.ptr(f32(sd[f"{td}.13.bias"]))
+        wh = torch.zeros(L.HEAD_PAD, L.DIM, dtype=torch.float32, device=dev)
+        wh[:L.HEAD] = sd[f"{td}.15.weight"]
+        hi, lo, f = split(wh)
+        self.c.head_w_hi, self.c.head_w_lo, self.c.head_w_f32 = L.ptr(hi), L.ptr(lo), L.ptr(f)
+        self.c.head_b = L.ptr(f32(sd[f"{td}.15.bias"]))
+        self.c.gn_w, self.c.gn_b = L.ptr(f32(sd["norm.weight"])), L.ptr(f32(sd["norm.bias"]))
+        self.c.upd_w, self.c.upd_b = L.ptr(f32(sd["ffeat_updater.0.weight"])), L.ptr(f32(sd["ffeat_updater.0.bias"]))
+        self.c.vis_w, self.c.vis_b = L.ptr(f32(sd["vis_predictor.0.weight"].reshape(-1))), L.ptr(f32(sd["vis_predictor.0.bias"]))
+
+
+class Workspace:
+    """Mixer activations for up to ``seqs`` particle tracks ((b, n) pairs)."""
+
+    def __init__(self, seqs: int, precision: int, device):
+        self.seqs = seqs
+        rows = _round_up(seqs * S_FRAMES, 128)
+        sq = _round_up(seqs, 128)
+        self.c = L.Workspace()
+        self.c.rows_alloc, self.c.seqs_alloc = rows, sq
+        self.keep: Dict[str, torch.Tensor] = {}
+
+        def alloc(name, r, c, dtype):
+            t = torch.zeros(r, c, dtype=dtype, device=device)
+            self.keep[name] = t
+            setattr(self.c, name, L.ptr(t))
+
+        alloc("x", rows, L.DIM, torch.float32)
+        alloc("delta", sq, L.HEAD, torch.float32)
+        if precision == L.PREC_F32:
+            alloc("x0_f32", rows, L.KPAD, torch.float32)
+            alloc("y_f32", rows, L.DIM, torch.float32)
+            alloc("h_f32", rows, L.HIDDEN, torch.float32)
+            alloc("p_f32", sq, L.DIM, torch.float32)
+        else:
+            parts = ("hi", "lo") if precision == L.PREC_BF16X3 else ("hi",)
+            for part in parts:
+                alloc(f"x0_{part}", rows, L.KPAD, torch.bfloat16)
+                alloc(f"y_{part}", rows, L.DIM, torch.bfloat16)
+                alloc(f"h_{part}", rows, L.HIDDEN, torch.bfloat16)
+                alloc(f"p_{part}", sq, L.DIM, torch.bfloat16)
+
+
+class Pyramid:
+    """4-level channels-last correlation pyramid (nets/pips.py:346-352)."""
+
+    def __init__(self, frames: int, H: int, W: int, feat_dtype: int, device):
+        self.frames, self.H, self.W, self.feat_dtype = frames, H, W, feat_dtype
+        self.f32, self.bf16 = [], []
+        h, w = H, W
+        for _ in range(L.LEVELS):
+            self.f32.append(torch.empty(frames, h, w, LATENT, dtype=torch.float32, device=device))
+            if feat_dtype == L.FEAT_BF16:
+                self.bf16.append(torch.empty(frames, h, w, LATENT, dtype=torch.bfloat16, device=device))
+            h, w = h // 2, w // 2
+        self.f32_ptrs = L.ptr_array(self.f32)
+        self.bf16_ptrs = L.ptr_array(self.bf16) if self.bf16 else None
+
+    def levels(self):
+        return self.bf16 if self.feat_dtype == L.FEAT_BF16 else self.f32
+
+    def build(self, fmaps: torch.Tensor, stream) -> None:
+        lib = L.load()
+        assert fmaps.dtype == torch.float32 and fmaps.is_contiguous()
+        L.check(lib.pips_pyramid_build(L.ptr(fmaps), self.frames, self.H, self.W, self.f32_ptrs,
+                                       self.bf16_ptrs, stream), "pips_pyramid_build")
+
+
+class RefineEngine:
+    """Runs the refinement loop for one model on one device."""
+
+    def __init__(self, precision: str = "bf16x3", feat_dtype: str = "fp32", max_seqs: int = 32768):
+        if precision not in L.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(L.PRECISIONS)}")
+        if feat_dtype not in L.FEAT_DTYPES:
+            raise ValueError(f"feat_dtype must be one of {sorted(L.FEAT_DTYPES)}")
+        self.precision = L.PRECISIONS[precision]
+        self.feat_dtype = L.FEAT_DTYPES[feat_dtype]
+        self.max_seqs = max_seqs
+        self._weights: Optional[PackedWeights] = None
+        self._weights_key = None
+        self._ws: Optional[Workspace] = None
+        self._pyr: Optional[Pyramid] = None
+        self._times = None
+        self.launches = 0                       # kernels launched by the last refine() call
+
+    # ------------------------------------------------------------------ caches
+    @staticmethod
+    def _stream() -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+    def weights(self, module) -> PackedWeights:
+        key = tuple((p.data_ptr(), p._version) for p in module.parameters())
+        if self._weights is None or key != self._weights_key:
+            self._weights = PackedWeights(module, self._stream())
+            self._weights_key = key
+        return self._weights
+
+    def workspace(self, seqs: int, device) -> Workspace:
+        if self._ws is None or self._ws.seqs < seqs or next(iter(self._ws.keep.values())).device != device:
+            self._ws = None
+            self._ws = Workspace(seqs, self.precision, device)
+        return self._ws
+
+    def pyramid(self, frames: int, H: int, W: int, device) -> Pyramid:
+        p = self._pyr
+        if p is None or (p.frames, p.H, p.W) != (frames, H, W) or p.f32[0].device != device:
+            self._pyr = None
+            self._pyr = Pyramid(frames, H, W, self.feat_dtype, device)
+        return self._pyr
+
+    def times(self, device) -> torch.Tensor:
+        if self._times is None or self._times.device != device:
+            # computed on the host exactly as the reference does (nets/pips.py:519); the sin/cos
+            # embedding multiplies it by up to 968.75, so the fp32 bit pattern matters
+            self._times = torch.linspace(0, S_FRAMES, S_FRAMES, dtype=torch.float32).to(device)
+        return self._times
+
+    # ------------------------------------------------------------------ the loop
+    def refine(self, module, fmaps: torch.Tensor, coords: torch.Tensor, feat_init: Optional[torch.Tensor],
+               iters: int, stride: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """fmaps (B,S,128,H8,W8) fp32, coords (B,S,N,2) fp32 in feature-map pixels.
+        Returns preds (iters,B,S,N,2) in input pixels, vis_e (B,S,N) logits, ffeat (B,N,128)."""
+        lib = L.load()
+        B, S, Cc, H8, W8 = fmaps.shape
+        if S != S_FRAMES or Cc != LATENT:
+            raise L.PipsCudaError(f"pips_b200 CUDA path supports S=8, C=128 (got S={S}, C={Cc})")
+        N = coords.shape[2]
+        dev = fmaps.device
+        st = self._stream()
+        w = self.weights(module)
+        pyr = self.pyramid(B * S, H8, W8, dev)
+        pyr.build(fmaps.reshape(B * S, Cc, H8, W8).contiguous(), st)
+        self.launches = 4
+        times = self.times(dev)
+        lvl = pyr.levels()
+
+        preds = torch.empty(iters, B, S, N, 2, dtype=torch.float32, device=dev)
+        vis = torch.empty(B, S, N, dtype=torch.float32, device=dev)
+        ffeat_out = torch.empty(B, N, LATENT, dtype=torch.float32, device=dev)
+        chunk = max(1, self.max_seqs // B)
+        for n0 in range(0, N, chunk):
+            n1 = min(N, n0 + chunk)
+            nc = n1 - n0
+            whole = nc == N
+            c = coords if whole else coords[:, :, n0:n1]
+            c = c.contiguous().clone()
+            c0 = c.clone()
+            ffeat = torch.empty(B * nc, LATENT, dtype=torch.float32, device=dev)
+            ffeats = torch.empty(B * nc, S, LATENT, dtype=torch.float32, device=dev)
+            if feat_init is None:
+                L.check(lib.pips_init_gather(L.ptr(pyr.f32[0]), B, S, nc, H8, W8, L.ptr(c), L.ptr(ffeat), L.ptr(ffeats), st),
+                        "pips_init_gather")
+                self.launches += 1
+            else:
+                fi = feat_init if whole else feat_init[:, n0:n1]
+                ffeat.copy_(fi.reshape(B * nc, LATENT))
+                ffeats.copy_(ffeat.unsqueeze(1).expand(-1, S, -1))
+            ws = self.workspace(B * nc, dev)
+            prob = L.Problem()
+            prob.B, prob.S, prob.N, prob.H, prob.W = B, S, nc, H8, W8
+            prob.feat_dtype, prob.precision = self.feat_dtype, self.precision
+            for i in range(L.LEVELS):
+                prob.lvl[i] = L.ptr(lvl[i])
+            prob.times, prob.coords, prob.coords0, prob.ffeats = L.ptr(times), L.ptr(c), L.ptr(c0), L.ptr(ffeats)
+            prob.stride = float(stride)
+            out = preds if whole else torch.empty(iters, B, S, nc, 2, dtype=torch.float32, device=dev)
+            for it in range(iters):
+                L.check(lib.pips_refine_iter(C.byref(prob), C.byref(w.c), C.byref(ws.c), L.ptr(out[it]), st),
+                        "pips_refine_iter")
+                self.launches += 1 + (1 + 3 * L.DEPTH + 2) + 1
+            v = vis if whole else torch.empty(B, S, nc, dtype=torch.float32, device=dev)
+            L.check(lib.pips_vis_head(L.ptr(ffeats), w.c.vis_w, w.c.vis_b, L.ptr(v), B, S, nc, st), "pips_vis_head")
+            self.launches += 1
+            if not whole:
+                preds[:, :, :, n0:n1] = out
+                vis[:, :, n0:n1] = v
+            ffeat_out[:, n0:n1] = ffeat.reshape(B, nc, LATENT)
+        return preds, vis, ffeat_out

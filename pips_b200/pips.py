@@ -1,0 +1,177 @@
+"""Drop-in for the reference's ``nets.pips.Pips`` (nets/pips.py:400-611).
+
+Same constructor, same ``forward(xys, rgbs, coords_init, feat_init, iters, trajs_g, vis_g, valids,
+sw, return_feat, is_train)`` signature and return tuples, same ``state_dict`` keys -- so ``demo.py``,
+``chain_demo.py``, ``test_on_*.py`` and ``saverloader.load`` work unchanged -- but at inference the
+per-iteration refinement loop (nets/pips.py:459-559) runs in hand-written sm_100a CUDA
+(libpips_b200.so) instead of ~150 eager torch ops per iteration, and the all-pairs correlation
+volume is never materialised.
+
+Extra, optional knobs (keyword-only; the reference signature is unchanged):
+  precision   'bf16x3' (default; tcgen05 with hi/lo-split bf16 operands, fp32-class accuracy, meets
+              the 1e-3 px parity target), 'bf16' (fast, ~1e-2 px), 'fp32' (CUDA-core GEMMs, exact)
+  feat_dtype  'fp32' (default) or 'bf16' storage of the correlation pyramid
+Environment overrides: PIPS_B200_PRECISION, PIPS_B200_FEAT.
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .encoder import Encoder
+from .engine import RefineEngine
+
+LATENT = 128
+CORR_LEVELS = 4
+CORR_RADIUS = 3
+
+
+class PreNormResidual(nn.Module):
+    def __init__(self, dim: int, fn: nn.Module):
+        super().__init__()
+        self.fn = fn
+        self.norm = nn.LayerNorm(dim)
+
+    def forward(self, x):
+        return self.fn(self.norm(x)) + x
+
+
+class _MeanOverFrames(nn.Module):
+    def forward(self, x):                      # (R, S, C) -> (R, C)
+        return x.mean(dim=1)
+
+
+def _feed_forward(dim: int, dense) -> nn.Sequential:
+    # indices 0 and 3 carry the parameters, like the reference's FeedForward (nets/pips.py:102-109);
+    # the Dropout(0.) slots are identities
+    return nn.Sequential(dense(dim, dim * 4), nn.GELU(), nn.Identity(), dense(dim * 4, dim), nn.Identity())
+
+
+def _conv1(cin, cout):
+    return nn.Conv1d(cin, cout, kernel_size=1)
+
+
+class DeltaBlock(nn.Module):
+    """MLP-Mixer over the S x 519 token stack of one track (nets/pips.py:283-311, :111-123)."""
+
+    def __init__(self, input_dim=LATENT, corr_levels=CORR_LEVELS, corr_radius=CORR_RADIUS, S=8, dim=512, depth=12):
+        super().__init__()
+        self.input_dim, self.S = input_dim, S
+        kitchen = corr_levels * (2 * corr_radius + 1) ** 2 + input_dim + 64 * 3 + 3
+        blocks = [nn.Sequential(PreNormResidual(dim, _feed_forward(S, _conv1)),
+                                PreNormResidual(dim, _feed_forward(dim, nn.Linear))) for _ in range(depth)]
+        self.to_delta = nn.Sequential(nn.Linear(kitchen, dim), *blocks, nn.LayerNorm(dim), _MeanOverFrames(),
+                                      nn.Linear(dim, S * (input_dim + 2)))
+
+    def forward(self, x):                      # x: (R, S, 519) already concatenated
+        return self.to_delta(x).reshape(x.shape[0], self.S, self.input_dim + 2)
+
+
+@contextlib.contextmanager
+def _strict_fp32():
+    """fnet runs in true fp32: torch enables TF32 convolutions by default on Ampere+, which alone
+    moves trajectories by ~1e-2 px."""
+    c, m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = c, m
+
+
+class Pips(nn.Module):
+    def __init__(self, S=8, stride=8, *, precision: Optional[str] = None, feat_dtype: Optional[str] = None,
+                 max_seqs: int = 32768):
+        super().__init__()
+        self.S = S
+        self.stride = stride
+        self.hidden_dim = 256
+        self.latent_dim = LATENT
+        self.corr_levels = CORR_LEVELS
+        self.corr_radius = CORR_RADIUS
+
+        self.fnet = Encoder(output_dim=LATENT, stride=stride)
+        self.delta_block = DeltaBlock(input_dim=LATENT, corr_levels=CORR_LEVELS, corr_radius=CORR_RADIUS, S=S)
+        self.norm = nn.GroupNorm(1, LATENT)
+        self.ffeat_updater = nn.Sequential(nn.Linear(LATENT, LATENT), nn.GELU())
+        self.vis_predictor = nn.Sequential(nn.Linear(LATENT, 1))
+
+        precision = precision or os.environ.get("PIPS_B200_PRECISION", "bf16x3")
+        feat_dtype = feat_dtype or os.environ.get("PIPS_B200_FEAT", "fp32")
+        self._engine = RefineEngine(precision=precision, feat_dtype=feat_dtype, max_seqs=max_seqs)
+        self._shard = None                      # (rank, world, group) when particle-sharded
+
+    # ------------------------------------------------------------------ configuration
+    @property
+    def engine(self) -> RefineEngine:
+        return self._engine
+
+    def shard_particles(self, group=None) -> "Pips":
+        """Particle-axis data parallelism: every rank owns N/G tracks and a
+        full copy of the feature pyramid; outputs are all-gathered so each rank returns the full
+        result.  Call after ``torch.distributed.init_process_group``."""
+        import torch.distributed as dist
+        self._shard = (dist.get_rank(group), dist.get_world_size(group), group)
+        return self
+
+    # ------------------------------------------------------------------ forward
+    def encode(self, rgbs: torch.Tensor) -> torch.Tensor:
+        """nets/pips.py:436-445: normalise to [-1,1], fnet per frame -> (B,S,128,H8,W8) fp32."""
+        B, S, C, H, W = rgbs.shape
+        x = 2 * (rgbs.float() / 255.0) - 1.0
+        with _strict_fp32():
+            fmaps = self.fnet(x.reshape(B * S, C, H, W))
+        return fmaps.reshape(B, S, self.latent_dim, H // self.stride, W // self.stride)
+
+    def forward(self, xys, rgbs, coords_init=None, feat_init=None, iters=3, trajs_g=None, vis_g=None, valids=None,
+                sw=None, return_feat=False, is_train=False):
+        B, N, D = xys.shape
+        assert (D == 2)
+        B, S, C, H, W = rgbs.shape
+
+        slow = trajs_g is not None or is_train or (sw is not None and getattr(sw, "save_this", False))
+        if slow:
+            from .torch_path import forward_torch
+            return forward_torch(self, xys, rgbs, coords_init=coords_init, feat_init=feat_init, iters=iters,
+                                 trajs_g=trajs_g, vis_g=vis_g, valids=valids, sw=sw, return_feat=return_feat,
+                                 is_train=is_train)
+        if not rgbs.is_cuda:
+            raise RuntimeError("pips_b200.Pips: the inference path is CUDA-only (sm_100a); move the model and "
+                               "inputs to a CUDA device. There is no CPU fallback.")
+        with torch.no_grad():
+            fmaps = self.encode(rgbs)
+            return self.refine(xys, fmaps, coords_init=coords_init, feat_init=feat_init, iters=iters,
+                               return_feat=return_feat)
+
+    def refine(self, xys, fmaps, coords_init=None, feat_init=None, iters=3, return_feat=False):
+        """Everything after fnet (nets/pips.py:450-611) given precomputed feature maps."""
+        B, N, _ = xys.shape
+        S = fmaps.shape[1]
+        stride = float(self.stride)
+        xys_ = xys.detach().float() / stride                                            # :450
+        if coords_init is None:
+            coords = xys_.reshape(B, 1, N, 2).repeat(1, S, 1, 1)                        # :453
+        else:
+            coords = coords_init.detach().float() / self.stride                         # :455
+        if feat_init is not None:
+            feat_init = feat_init.detach().float()
+
+        if self._shard is None or self._shard[1] == 1:
+            preds, vis_e, ffeat = self._engine.refine(self, fmaps.float(), coords, feat_init, iters, stride)
+        else:
+            from .sharding import refine_sharded
+            preds, vis_e, ffeat = refine_sharded(self, fmaps.float(), coords, feat_init, iters, stride)
+
+        start = coords * stride
+        coord_predictions = [preds[i] for i in range(iters)]                            # :538
+        last = coord_predictions[-1] if iters > 0 else start
+        coord_predictions2 = [start, start] + coord_predictions + [last, last]          # :474-475, :562-563
+        losses = None
+        if return_feat:
+            return coord_predictions, coord_predictions2, vis_e, ffeat, losses
+        return coord_predictions, coord_predictions2, vis_e, losses

@@ -1,0 +1,51 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol of include/pips_b200.h;
+the module mirrors the reference's state_dict; error paths do not need a GPU."""
+import os
+import re
+
+import torch
+
+from oracle import pips_oracle as po
+from pips_b200 import Pips, _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_are_exported():
+    hdr = open(os.path.join(ROOT, "include", "pips_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(pips_\w+)\s*\(", hdr, flags=re.M))
+    assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
+    lib = L.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.pips_abi_version() == 1
+
+
+def test_argument_validation_without_gpu():
+    lib = L.load()
+    assert lib.pips_gemm_tc(0, 0, 512, 128, 0, 0, 512, 256, 128, 256, 100, 0, 0, 0, 0, 0, 0, 0, 0) != 0
+    assert b"multiple of 64" in lib.pips_last_error()
+    assert lib.pips_corr_gather(None, 0, 1, 7, 1, 16, 16, 0, 0, 0, 0, 0, 0, 576, 0) != 0
+    assert lib.pips_refine_iter(None, None, None, 0, 0) != 0
+
+
+def test_state_dict_contract_matches_reference_spec():
+    m = Pips(S=8, stride=4)
+    spec = dict(po.state_dict_spec())
+    sd = m.state_dict()
+    assert list(sd) == [k for k, _ in po.state_dict_spec()]          # same names, same order
+    assert all(tuple(v.shape) == spec[k] for k, v in sd.items())
+    m.load_state_dict(po.init_state_dict(0), strict=True)
+    assert sum(p.numel() for p in m.parameters()) == 28677713
+
+
+def test_torch_modules_equal_oracle_on_cpu():
+    sd = po.init_state_dict(1)
+    m = Pips(S=8, stride=8).eval()
+    m.load_state_dict(sd)
+    x = torch.randn(3, 8, 519)
+    with torch.no_grad():
+        assert (m.delta_block(x) - po.mixer(sd, x).reshape(3, 8, 130)).abs().max() < 1e-6
+        rgb = po.smooth_video(1, 2, 64, 96)
+        inp = (2 * (rgb / 255) - 1).reshape(2, 3, 64, 96)
+        assert (m.fnet(inp) - po.fnet(sd, inp, 8)).abs().max() < 1e-6

@@ -1,0 +1,91 @@
+"""End-to-end parity of pips_b200.Pips.forward (CUDA) against the reference's recorded outputs
+(tests/golden) and the CPU oracle, through the public module API (B200 only)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pips_oracle as po
+from pips_b200 import Pips
+from tests.golden.make_golden import CASES, case_inputs
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.npz"))
+
+# tolerance in input pixels on trajs (BASELINE.json north_star: 1e-3 max-abs)
+TOL = {"fp32": 1e-3, "bf16x3": 1e-3, "bf16": 0.25}
+
+
+def _run(name, precision, feat="fp32"):
+    c = CASES[name]
+    sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+    model = Pips(S=8, stride=c["stride"], precision=precision, feat_dtype=feat).to(DEV).eval()
+    model.load_state_dict(sd, strict=True)
+    rgbs, xys, extra = case_inputs(c)
+    extra = {k: v.to(DEV) for k, v in extra.items()}
+    with torch.no_grad():
+        out = model(xys.to(DEV), rgbs.to(DEV), iters=c["iters"], return_feat=True, **extra)
+    torch.cuda.synchronize()
+    return c, out
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+def test_forward_matches_reference_golden(name, precision):
+    c, (preds, preds2, vis_e, ffeat, losses) = _run(name, precision)
+    assert losses is None and len(preds) == c["iters"] and len(preds2) == c["iters"] + 4
+    got = torch.stack(preds).cpu().numpy()
+    ref = GOLD[name + "/preds"]
+    err = np.abs(got - ref).reshape(c["iters"], -1).max(1)
+    print(f"{name} {precision}: per-iter max|d trajs| px = {err}")
+    tol = TOL[precision] * (5 if c["head_scale"] >= 1.0 else 1)
+    assert err.max() < tol, err
+    assert np.abs(ffeat.cpu().numpy() - GOLD[name + "/ffeat"]).max() < 1e-4
+    vtol = 5e-3 if precision != "bf16" else 0.5
+    assert np.abs(vis_e.cpu().numpy() - GOLD[name + "/vis_e"]).max() < vtol
+    assert torch.equal(preds2[0], preds2[1]) and torch.equal(preds2[-1], preds[-1])
+
+
+def test_bf16_features_are_close():
+    c, (preds, _, _, _, _) = _run("tiny_s8", "bf16x3", feat="bf16")
+    err = np.abs(torch.stack(preds).cpu().numpy() - GOLD["tiny_s8/preds"]).max()
+    print("bf16 features, bf16x3 mixer: max err px", err)
+    assert err < 5e-2
+
+
+def test_teacher_forced_single_iteration_vs_oracle():
+    """One iteration from identical state, larger N than the golden cases, oracle live on CPU."""
+    c = dict(B=2, H=128, W=160, N=300, stride=8, iters=1, head_scale=0.05, seed=9, oob=True, warm=True)
+    sd = po.init_state_dict(seed=9, head_scale=0.05)
+    rgbs, xys, extra = case_inputs(c)
+    with torch.no_grad():
+        ref = po.forward(sd, xys, rgbs, iters=1, stride=8, return_feat=True, **extra)
+    model = Pips(S=8, stride=8).to(DEV).eval()
+    model.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        got = model(xys.to(DEV), rgbs.to(DEV), iters=1, return_feat=True, **{k: v.to(DEV) for k, v in extra.items()})
+    err = (got[0][0].cpu() - ref[0][0]).abs().max().item()
+    print("teacher-forced 1 iter, N=300: max err px", err)
+    assert err < 1e-3
+    assert (got[2].cpu() - ref[2]).abs().max() < 5e-3
+
+
+def test_particle_chunking_is_transparent():
+    c = CASES["rect_s4_oob"]
+    sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+    rgbs, xys, _ = case_inputs(c)
+    outs = []
+    for max_seqs in (32768, 2 * 7):               # second: chunks of 7 particles
+        model = Pips(S=8, stride=c["stride"], max_seqs=max_seqs).to(DEV).eval()
+        model.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            outs.append(torch.stack(model(xys.to(DEV), rgbs.to(DEV), iters=3)[0]).cpu())
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_cpu_inputs_fail_loudly():
+    model = Pips(S=8, stride=8).eval()
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        model(torch.zeros(1, 4, 2), torch.zeros(1, 8, 3, 64, 64), iters=1)

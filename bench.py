@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Benchmark of the PIPs refinement hot path (BASELINE.json metric: particle-frame updates/s).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5            # this repo's CUDA path on 1 GPU
+    torchrun ... bench.py --gpus N ...                        # one rank per GPU, particle-sharded (weak scaling)
+    python bench.py --impl reference ...                      # the reference algorithm on the host CPU cores
+
+A step is one ``Pips.forward(xys, rgbs, iters=6)`` over one synthetic batch:
+  N=1   BASELINE configs[1]: B=4, S=8, 384x512, N=1024, iters=6, stride 8
+  N>1   per-GPU work fixed (1024 particles per rank), global N = 1024*G (G=4 is configs[2], N=4096)
+``value`` counts B*S*N_global*iters updates per second of the max-over-ranks device time with the
+inputs resident in HBM; ``e2e`` runs the same call from pinned host buffers with the H2D / D2H copies
+inside the timed region.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B, S, H, W, N_PER_GPU, ITERS, STRIDE = 4, 8, 384, 512, 1024, 6, 8
+UNIT_FLOP = 51.78e6                       # mixer matmul FLOPs per particle-frame update
+METRIC = "particle_frame_updates_per_sec"
+UNIT = "updates/s"
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update({k: float(m[k]) for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in m})
+        p["source"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(n_global: int):
+    from oracle import pips_oracle as po          # input generator + weights only (not on the measured path)
+    rgbs = po.smooth_video(B, S, H, W, seed=1234).to(torch.bfloat16)       # integers 0..255: exact in bf16
+    xys = po.random_queries(B, n_global, H, W, seed=4321)
+    sd = po.init_state_dict(seed=0, head_scale=0.05)
+    return sd, rgbs, xys
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    """The reference's algorithm (all-pairs volume, dense heat-map, fp32 torch ops -- nets/pips.py:428-611
+    restated in oracle/pips_oracle.py; the reference itself is Python and cannot travel to the GPU box) on
+    the host CPU cores, on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from oracle import pips_oracle as po
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd, rgbs, xys = make_inputs(N_PER_GPU)
+    bs, ns = 1, 256                                # reference-style chunk (test_on_davis.py:111-125 chunks N by 256)
+    rg, xy = rgbs[:bs].float(), xys[:bs, :ns]
+
+    def step():
+        with torch.no_grad():
+            po.forward(sd, xy, rg, iters=ITERS, stride=STRIDE, allpairs=True, faithful_dead_work=True)
+
+    t0 = time.perf_counter(); step(); first = time.perf_counter() - t0
+    budget = 200.0
+    steps, warm = args.steps, args.warmup
+    if first * (steps + warm) > budget:
+        steps = max(1, int(budget / first) - 1); warm = 1 if steps > 1 else 0
+    for _ in range(max(0, warm - 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    val = bs * S * ns * ITERS / dt
+    sample = f"B={bs} of {B}, N={ns} of {N_PER_GPU}, iters={ITERS}, incl. fnet, all-pairs volume + dense heat-map as the reference computes them"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cfg2 sample: {sample}", "stride": STRIDE},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def cpu_baseline_leg():
+    from oracle import pips_oracle as po
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd, rgbs, xys = make_inputs(N_PER_GPU)
+    bs, ns = 1, 256
+    rg, xy = rgbs[:bs].float(), xys[:bs, :ns]
+    with torch.no_grad():
+        po.forward(sd, xy, rg, iters=1, stride=STRIDE, allpairs=True)          # warm caches / threads
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 2 or (time.perf_counter() - t0 < 10.0 and reps < 8):
+            po.forward(sd, xy, rg, iters=ITERS, stride=STRIDE, allpairs=True, faithful_dead_work=True)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+    return {"value": bs * S * ns * ITERS / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"B={bs} of {B}, N={ns} of {N_PER_GPU}, iters={ITERS}, {reps} forwards incl. fnet, reference algorithm (all-pairs volume + dense heat-map)"}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from pips_b200 import Pips
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    n_global = N_PER_GPU * world
+    sd, rgbs_h, xys_h = make_inputs(n_global)
+    model = Pips(S=S, stride=STRIDE, precision=args.precision, feat_dtype=args.feat).to(dev).eval()
+    model.load_state_dict(sd, strict=True)
+    if world > 1:
+        model.shard_particles()
+    rgbs_h, xys_h = rgbs_h.pin_memory(), xys_h.pin_memory()
+    rgbs, xys = rgbs_h.to(dev), xys_h.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)             # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        with torch.no_grad():
+            return model(xys, rgbs, iters=ITERS)
+
+    def step_host():
+        with torch.no_grad():
+            out = model(xys_h.to(dev, non_blocking=True), rgbs_h.to(dev, non_blocking=True), iters=ITERS)
+            return out[0][-1].cpu(), out[2].cpu()
+
+    def timed(step, k):
+        evs = []
+        for _ in range(k):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); step(); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs) / 1e3
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_dev = timed(step_device, args.steps)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = model.engine.launches * args.steps
+    step_host()
+    barrier()
+    t_e2e = timed(step_host, args.steps)
+    barrier()
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = t.tolist()
+    if rank != 0:
+        return
+
+    updates = B * S * n_global * ITERS
+    pk = peaks()
+    # per-kernel timing of one iteration, live, same buffers (CUDA events around every launch)
+    with torch.no_grad():
+        fmaps = model.encode(rgbs)
+        coords = (xys[:, :N_PER_GPU] / STRIDE).reshape(B, 1, N_PER_GPU, 2).repeat(1, S, 1, 1)
+        prof, dims = model.engine.profile_iteration(model, fmaps.float(), coords, STRIDE, reps=3)
+    mean = {k: statistics.mean(v) for k, v in prof.items()}
+    per_iter = {k: sum(v) / 3 for k, v in prof.items()}
+    M = dims["M"]
+    gemm_ms = per_iter["gemm_fc1"] + per_iter["gemm_fc2"]
+    gemm_flop = 2.0 * M * 2048 * 512 * 2 * 12
+    achieved_tf = gemm_flop / (gemm_ms * 1e-3) / 1e12
+    tc = args.precision != "fp32"
+    mma_per_product = 3 if args.precision == "bf16x3" else 1
+    roofline = {"kernel": "gemm_tc_kernel (FC1+FC2 of the 12 channel-mixing blocks)" if tc else "gemm_f32_kernel",
+                "bound": "tensor", "achieved": achieved_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved_tf / pk["bf16_tflops_sustained"], "traffic": None,
+                "peak_source": pk["source"] + " (sustained bf16 cuBLAS)", "share_of_iteration": gemm_ms / sum(per_iter.values()),
+                "mma_issued_frac": achieved_tf * mma_per_product / pk["bf16_tflops_sustained"] if tc else None}
+    e_f = 4 if args.feat == "fp32" else 2
+    e_o = {"fp32": 4, "bf16x3": 4, "bf16": 2}[args.precision]
+    unit_bytes = 4 * 64 * 128 * e_f + 128 * 4 + 576 * e_o
+    corr_gbs = unit_bytes * (M) / (mean["corr_gather"] * 1e-3) / 1e9
+    roofline_corr = {"kernel": "corr_gather_kernel", "bound": "hbm", "achieved": corr_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": corr_gbs / pk["hbm_gbs"], "traffic": None, "bytes_per_unit": unit_bytes,
+                     "peak_source": pk["source"] + " (copy bandwidth)", "note": "pyramid is L2-resident at this config"}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tr = json.load(f)
+        roofline["traffic"] = tr.get("gemm_tc_bytes_per_launch")
+        roofline_corr["traffic"] = tr.get("corr_gather_bytes_per_launch")
+    except Exception:
+        pass
+    cpu = cpu_baseline_leg() if world == 1 and not args.no_cpu_baseline else None
+    h2d = rgbs_h.numel() * rgbs_h.element_size() + xys_h.numel() * 4
+    d2h = (B * S * n_global * 2 + B * S * n_global) * 4
+    line = {"metric": METRIC, "value": updates / (t_dev / args.steps), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (hi/lo split, fp32 accumulate) + f32", "bf16": "bf16"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": f"BASELINE cfg2 per GPU: B={B}, S={S}, {H}x{W} bf16 video, N={N_PER_GPU}/GPU (global N={n_global}), iters={ITERS}, stride={STRIDE}",
+                       "precision": args.precision, "feat_dtype": args.feat, "parallelism": f"particle-sharded dp{world}" if world > 1 else "single GPU",
+                       "includes": "fnet + pyramid + 6 refinement iterations + vis head", "l2": "256 MB write between steps (L2 flushed); working set > L2"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": updates / (t_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": t_e2e / args.steps * 1e3},
+            "roofline": roofline, "roofline_corr": roofline_corr,
+            "kernel_ms_per_iteration": {k: round(v, 4) for k, v in per_iter.items()},
+            "loop_only": {"ms_per_iteration": sum(per_iter.values()), "updates_per_s": B * S * N_PER_GPU / (sum(per_iter.values()) * 1e-3)},
+            "whole_path_tensor_frac": (updates * UNIT_FLOP / (t_dev / args.steps)) / 1e12 / pk["bf16_tflops_sustained"] / world}
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("PIPS_B200_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--feat", default=os.environ.get("PIPS_B200_FEAT", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -193,9 +193,11 @@ class RefineEngine:
 
     # ------------------------------------------------------------------ the loop
     def refine(self, module, fmaps: torch.Tensor, coords: torch.Tensor, feat_init: Optional[torch.Tensor],
-               iters: int, stride: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+               iters: int, stride: float, on_iter=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """fmaps (B,S,128,H8,W8) fp32, coords (B,S,N,2) fp32 in feature-map pixels.
-        Returns preds (iters,B,S,N,2) in input pixels, vis_e (B,S,N) logits, ffeat (B,N,128)."""
+        Returns preds (iters,B,S,N,2) in input pixels, vis_e (B,S,N) logits, ffeat (B,N,128).
+        ``on_iter(it, coords_px)`` (optional) is called right after iteration ``it`` has been enqueued,
+        when the particles fit one chunk -- the sharded path hangs its per-iteration all-gather there."""
         lib = L.load()
         B, S, Cc, H8, W8 = fmaps.shape
         if S != S_FRAMES or Cc != LATENT:
@@ -244,6 +246,8 @@ class RefineEngine:
                 L.check(lib.pips_refine_iter(C.byref(prob), C.byref(w.c), C.byref(ws.c), L.ptr(out[it]), st),
                         "pips_refine_iter")
                 self.launches += 1 + (1 + 3 * L.DEPTH + 2) + 1
+                if on_iter is not None and whole:
+                    on_iter(it, out[it])
             v = vis if whole else torch.empty(B, S, nc, dtype=torch.float32, device=dev)
             L.check(lib.pips_vis_head(L.ptr(ffeats), w.c.vis_w, w.c.vis_b, L.ptr(v), B, S, nc, st), "pips_vis_head")
             self.launches += 1
@@ -252,3 +256,72 @@ class RefineEngine:
                 vis[:, :, n0:n1] = v
             ffeat_out[:, n0:n1] = ffeat.reshape(B, nc, LATENT)
         return preds, vis, ffeat_out
+
+    # ------------------------------------------------------------------ instrumentation
+    def profile_iteration(self, module, fmaps: torch.Tensor, coords: torch.Tensor, stride: float, reps: int = 3):
+        """Re-runs one refinement iteration kernel by kernel (the same launches pips_refine_iter makes,
+        same buffers, back to back) with CUDA events around every launch.  Returns
+        {kernel class: [ms, ...]} -- the source of the live roofline numbers in bench.py."""
+        lib = L.load()
+        B, S, Cc, H8, W8 = fmaps.shape
+        N = coords.shape[2]
+        if B * N > self.max_seqs:
+            N = self.max_seqs // B
+            coords = coords[:, :, :N]
+        dev = fmaps.device
+        st = self._stream()
+        w = self.weights(module).c
+        pyr = self.pyramid(B * S, H8, W8, dev)
+        pyr.build(fmaps.reshape(B * S, Cc, H8, W8).contiguous(), st)
+        lvl = L.ptr_array(pyr.levels())
+        c = coords.contiguous().clone()
+        c0 = c.clone()
+        ffeat = torch.empty(B * N, LATENT, dtype=torch.float32, device=dev)
+        ffeats = torch.empty(B * N, S, LATENT, dtype=torch.float32, device=dev)
+        L.check(lib.pips_init_gather(L.ptr(pyr.f32[0]), B, S, N, H8, W8, L.ptr(c), L.ptr(ffeat), L.ptr(ffeats), st))
+        ws = self.workspace(B * N, dev).c
+        times = self.times(dev)
+        out = torch.empty(B, S, N, 2, dtype=torch.float32, device=dev)
+        seqs, M = B * N, B * N * S
+        f32, x3 = self.precision == L.PREC_F32, self.precision == L.PREC_BF16X3
+        rec: Dict[str, list] = {}
+
+        def timed(name, fn):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.check(fn(), name)
+            e1.record()
+            rec.setdefault(name, []).append((e0, e1))
+
+        def dense(name, a, lda, a_rows, wt, ldw, w_rows, Mv, Nv, Kv, bias, epi, o32, ldo, oh, ldh):
+            if f32:
+                o = oh[2] if epi == L.EPI_BIAS_GELU else o32
+                ld = ldh if epi == L.EPI_BIAS_GELU else ldo
+                timed(name, lambda: lib.pips_gemm_f32(a[2], lda, wt[2], ldw, Mv, Nv, Kv, bias, epi, o, ld, st))
+            else:
+                timed(name, lambda: lib.pips_gemm_tc(a[0], a[1] if x3 else None, lda, a_rows, wt[0], wt[1] if x3 else None, ldw,
+                                                     w_rows, Mv, Nv, Kv, bias, epi, o32, ldo, oh[0], oh[1] if x3 else None, ldh, st))
+
+        for _ in range(reps):
+            timed("corr_gather", lambda: lib.pips_corr_gather(
+                lvl, self.feat_dtype, B, S, N, H8, W8, L.ptr(c), L.ptr(ffeats), L.ptr(times),
+                None if f32 else ws.x0_hi, ws.x0_lo if x3 else None, ws.x0_f32 if f32 else None, L.KPAD, st))
+            dense("gemm_in", (ws.x0_hi, ws.x0_lo, ws.x0_f32), L.KPAD, ws.rows_alloc, (w.in_w_hi, w.in_w_lo, w.in_w_f32), L.KPAD,
+                  L.DIM, M, L.DIM, L.KPAD, w.in_b, L.EPI_BIAS, ws.x, L.DIM, (None, None, None), 0)
+            for l in range(L.DEPTH):
+                lw = w.layer[l]
+                timed("tokenmix", lambda: lib.pips_tokenmix(
+                    ws.x, seqs, lw.ln1_w, lw.ln1_b, lw.tok_w1, lw.tok_b1, lw.tok_w2, lw.tok_b2, lw.ln2_w, lw.ln2_b,
+                    None if f32 else ws.y_hi, ws.y_lo if x3 else None, ws.y_f32 if f32 else None, st))
+                dense("gemm_fc1", (ws.y_hi, ws.y_lo, ws.y_f32), L.DIM, ws.rows_alloc, (lw.fc1_w_hi, lw.fc1_w_lo, lw.fc1_w_f32),
+                      L.DIM, L.HIDDEN, M, L.HIDDEN, L.DIM, lw.fc1_b, L.EPI_BIAS_GELU, None, 0, (ws.h_hi, ws.h_lo, ws.h_f32), L.HIDDEN)
+                dense("gemm_fc2", (ws.h_hi, ws.h_lo, ws.h_f32), L.HIDDEN, ws.rows_alloc, (lw.fc2_w_hi, lw.fc2_w_lo, lw.fc2_w_f32),
+                      L.HIDDEN, L.DIM, M, L.DIM, L.HIDDEN, lw.fc2_b, L.EPI_BIAS_RESID, ws.x, L.DIM, (None, None, None), 0)
+            timed("ln_pool", lambda: lib.pips_ln_pool(ws.x, seqs, w.out_ln_w, w.out_ln_b, None if f32 else ws.p_hi,
+                                                      ws.p_lo if x3 else None, ws.p_f32 if f32 else None, st))
+            dense("gemm_head", (ws.p_hi, ws.p_lo, ws.p_f32), L.DIM, ws.seqs_alloc, (w.head_w_hi, w.head_w_lo, w.head_w_f32), L.DIM,
+                  L.HEAD_PAD, seqs, L.HEAD, L.DIM, w.head_b, L.EPI_BIAS, ws.delta, L.HEAD, (None, None, None), 0)
+            timed("update", lambda: lib.pips_update(ws.delta, L.ptr(c), L.ptr(c0), L.ptr(ffeats), w.gn_w, w.gn_b, w.upd_w, w.upd_b,
+                                                    L.ptr(out), float(stride), B, S, N, st))
+        torch.cuda.synchronize()
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in rec.items()}, dict(B=B, S=S, N=N, M=M)

@@ -1,0 +1,75 @@
+"""Particle-axis sharding over the GPUs of one node.
+
+Tracks are independent -- the mixer mixes over the S frames and the channels of one track, never
+across particles (nets/pips.py:517-524) -- so rank g refines particles [g*N/G, (g+1)*N/G) against its
+own full copy of the feature pyramid and the only exchange is one small all-gather of the new
+coordinates per iteration (<= 1 MB at the BASELINE configs) plus the visibility logits at the end.
+The gathers are issued asynchronously on NCCL's stream (``async_op=True``): iteration i+1 does not
+depend on them, so they overlap the next iteration's kernels.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(N: int, rank: int, world: int) -> Tuple[int, int, int]:
+    """Equal-size shards of ceil(N/world) particles (the tail is padded by repeating the last track)."""
+    per = (N + world - 1) // world
+    n0 = min(rank * per, N)
+    n1 = min(n0 + per, N)
+    return n0, n1, per
+
+
+def _pad_particles(t: torch.Tensor, dim: int, per: int) -> torch.Tensor:
+    n = t.shape[dim]
+    if n == per:
+        return t.contiguous()
+    if n == 0:
+        shape = list(t.shape)
+        shape[dim] = per
+        return torch.zeros(shape, dtype=t.dtype, device=t.device)
+    last = t.narrow(dim, n - 1, 1)
+    reps = [1] * t.dim()
+    reps[dim] = per - n
+    return torch.cat([t, last.repeat(*reps)], dim=dim).contiguous()
+
+
+def refine_sharded(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_init: Optional[torch.Tensor], iters: int,
+                   stride: float):
+    rank, world, group = model._shard
+    B, S, N, _ = coords.shape
+    n0, n1, per = shard_bounds(N, rank, world)
+    my_coords = _pad_particles(coords[:, :, n0:n1], 2, per)
+    my_feat = None if feat_init is None else _pad_particles(feat_init[:, n0:n1], 1, per)
+
+    dev = coords.device
+    # (world, iters, B, S, per, 2): one gather per iteration, issued as soon as that iteration is enqueued
+    gathered = torch.empty(world, iters, B, S, per, 2, dtype=torch.float32, device=dev)
+    works = []
+
+    def gather_iter(it, coords_px):
+        out = torch.empty(world * B, S, per, 2, dtype=torch.float32, device=dev)     # concatenated along dim 0
+        works.append((dist.all_gather_into_tensor(out, coords_px, group=group, async_op=True), out.view(world, B, S, per, 2), it))
+
+    preds, vis, ffeat = model.engine.refine(model, fmaps, my_coords, my_feat, iters, stride, on_iter=gather_iter)
+    if len(works) != iters:                      # particles were chunked inside the engine: gather at the end
+        works.clear()
+        for it in range(iters):
+            gather_iter(it, preds[it].contiguous())
+    vis_cat = torch.empty(world * B, S, per, dtype=torch.float32, device=dev)
+    wv = dist.all_gather_into_tensor(vis_cat, vis.contiguous(), group=group, async_op=True)
+    ff_cat = torch.empty(world * B, per, ffeat.shape[-1], dtype=torch.float32, device=dev)
+    wf = dist.all_gather_into_tensor(ff_cat, ffeat.contiguous(), group=group, async_op=True)
+    vis_all, ff_all = vis_cat.view(world, B, S, per), ff_cat.view(world, B, per, -1)
+    for wk, out, it in works:
+        wk.wait()
+        gathered[:, it] = out
+    wv.wait()
+    wf.wait()
+    preds_full = gathered.permute(1, 2, 3, 0, 4, 5).reshape(iters, B, S, world * per, 2)[:, :, :, :N].contiguous()
+    vis_full = vis_all.permute(1, 2, 0, 3).reshape(B, S, world * per)[:, :, :N].contiguous()
+    ff_full = ff_all.permute(1, 0, 2, 3).reshape(B, world * per, -1)[:, :N].contiguous()
+    return preds_full, vis_full, ff_full

@@ -259,16 +259,17 @@ def test_update_and_vis_head():
     d = lambda t: t.to(DEV).contiguous()
     dd, cd, c0d, fd = d(delta.reshape(B * N, S * 130)), d(coords), d(coords0), d(ffeats)
     out = torch.empty(B, S, N, 2, device=DEV)
-    L.check(lib.pips_update(L.ptr(dd), L.ptr(cd), L.ptr(c0d), L.ptr(fd), L.ptr(d(sd["norm.weight"])), L.ptr(d(sd["norm.bias"])),
-                            L.ptr(d(sd["ffeat_updater.0.weight"])), L.ptr(d(sd["ffeat_updater.0.bias"])), L.ptr(out), 4.0,
+    # keep the device copies alive: a temporary's block would be recycled by the caching allocator
+    gw, gb, wu, bu = d(sd["norm.weight"]), d(sd["norm.bias"]), d(sd["ffeat_updater.0.weight"]), d(sd["ffeat_updater.0.bias"])
+    L.check(lib.pips_update(L.ptr(dd), L.ptr(cd), L.ptr(c0d), L.ptr(fd), L.ptr(gw), L.ptr(gb), L.ptr(wu), L.ptr(bu), L.ptr(out), 4.0,
                             B, S, N, _st()))
     _sync_check()
     assert (cd.cpu() - c_ref).abs().max() < 1e-6
     assert (out.cpu() - c_ref * 4.0).abs().max() < 1e-5
     assert (fd.cpu().reshape(-1, 128) - ff_ref).abs().max() < 2e-5
     vis = torch.empty(B, S, N, device=DEV)
-    L.check(lib.pips_vis_head(L.ptr(fd), L.ptr(d(sd["vis_predictor.0.weight"].reshape(-1))), L.ptr(d(sd["vis_predictor.0.bias"])),
-                              L.ptr(vis), B, S, N, _st()))
+    vw, vb = d(sd["vis_predictor.0.weight"].reshape(-1)), d(sd["vis_predictor.0.bias"])
+    L.check(lib.pips_vis_head(L.ptr(fd), L.ptr(vw), L.ptr(vb), L.ptr(vis), B, S, N, _st()))
     _sync_check()
     v_ref = torch.nn.functional.linear(ff_ref, sd["vis_predictor.0.weight"], sd["vis_predictor.0.bias"]).reshape(B, N, S).permute(0, 2, 1)
     assert (vis.cpu() - v_ref).abs().max() < 1e-4

@@ -1,0 +1,76 @@
+"""Host logic of the particle-sharded path with world_size 2 on CPU (gloo): shard bounds, tail
+padding, per-iteration all-gather and reassembly.  The CUDA engine is replaced by a deterministic
+stand-in (the kernels themselves are covered by the -m gpu tests)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pips_b200.sharding import refine_sharded, shard_bounds
+
+
+def test_shard_bounds_cover_all_particles():
+    for N in (1, 7, 8, 1024, 1025):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                n0, n1, per = shard_bounds(N, r, world)
+                assert 0 <= n0 <= n1 <= N and n1 - n0 <= per
+                seen += list(range(n0, n1))
+            assert seen == list(range(N))
+
+
+class _FakeEngine:
+    def refine(self, module, fmaps, coords, feat_init, iters, stride, on_iter=None):
+        B, S, n, _ = coords.shape
+        preds = torch.stack([coords * stride + (it + 1) for it in range(iters)])
+        for it in range(iters):
+            if on_iter is not None:
+                on_iter(it, preds[it].contiguous())
+        vis = coords.sum(-1)
+        ffeat = coords[:, 0, :, :1].repeat(1, 1, 128) if feat_init is None else feat_init * 2
+        return preds, vis, ffeat
+
+
+class _FakeModel:
+    def __init__(self, shard):
+        self._shard = shard
+        self.engine = _FakeEngine()
+
+
+def _worker(rank, world, port, N, use_feat, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        B, S, iters = 2, 8, 3
+        coords = torch.randn(B, S, N, 2)
+        feat = torch.randn(B, N, 128) if use_feat else None
+        model = _FakeModel((rank, world, None))
+        preds, vis, ff = refine_sharded(model, torch.zeros(B, S, 128, 4, 4), coords, feat, iters, 4.0)
+        exp_p, exp_v, exp_f = _FakeEngine().refine(None, None, coords, feat, iters, 4.0)
+        ok = torch.equal(preds, exp_p) and torch.equal(vis, exp_v) and torch.equal(ff, exp_f)
+        q.put((rank, bool(ok), tuple(preds.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("N,use_feat", [(10, False), (7, True), (1, False)])
+def test_refine_sharded_world2_gloo(N, use_feat):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, N, use_feat, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
+    assert all(shape == (3, 2, 8, N, 2) for _, _, shape in res)

@@ -32,6 +32,17 @@ CASES = {
 }
 
 
+LOSS_CASE = dict(B=2, H=128, W=128, N=9, stride=8, iters=3, head_scale=0.05, seed=6, oob=False, warm=False)
+
+
+def loss_targets(c, xys):
+    g = torch.Generator().manual_seed(400 + c["seed"])
+    trajs_g = xys[:, None] + torch.cumsum(torch.randn(c["B"], 8, c["N"], 2, generator=g), 1)
+    vis_g = (torch.rand(c["B"], 8, c["N"], generator=g) > 0.3).float()
+    valids = (torch.rand(c["B"], 8, c["N"], generator=g) > 0.1).float()
+    return trajs_g, vis_g, valids
+
+
 def case_inputs(c):
     """Shared with tests/: deterministic inputs for a golden case."""
     rgbs = po.smooth_video(c["B"], 8, c["H"], c["W"], seed=100 + c["seed"])
@@ -72,6 +83,20 @@ def main():
         out[name + "/ffeat"] = ffeat.numpy()
         print(name, "trajs_e range", float(preds[-1].min()), float(preds[-1].max()),
               "mean |d| from init", float((preds[-1] - xys[:, None]).abs().mean()))
+    # supervised call (nets/pips.py:600-606): losses + is_train semantics, consumed by the torch path tests
+    for name, is_train in (("loss_s8", False), ("train_s8", True)):
+        c = LOSS_CASE
+        sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+        model = Pips(S=8, stride=c["stride"]).eval()
+        model.load_state_dict(sd, strict=True)
+        rgbs, xys, extra = case_inputs(c)
+        trajs_g, vis_g, valids = loss_targets(c, xys)
+        with torch.no_grad():
+            preds, _, vis_e, losses = model(xys, rgbs, iters=c["iters"], trajs_g=trajs_g, vis_g=vis_g, valids=valids, is_train=is_train)
+        out[name + "/preds"] = torch.stack(preds).numpy()
+        out[name + "/vis_e"] = vis_e.numpy()
+        out[name + "/losses"] = np.array([float(l) for l in losses], dtype=np.float64)
+        print(name, "losses", out[name + "/losses"])
     np.savez_compressed(os.path.join(HERE, "reference_outputs.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_outputs.npz"))
 

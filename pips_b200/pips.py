@@ -11,7 +11,9 @@ Extra, optional knobs (keyword-only; the reference signature is unchanged):
   precision   'bf16x3' (default; tcgen05 with hi/lo-split bf16 operands, fp32-class accuracy, meets
               the 1e-3 px parity target), 'bf16' (fast, ~1e-2 px), 'fp32' (CUDA-core GEMMs, exact)
   feat_dtype  'fp32' (default) or 'bf16' storage of the correlation pyramid
-Environment overrides: PIPS_B200_PRECISION, PIPS_B200_FEAT.
+  fnet_mode   'x3' (default; cuDNN TF32 tensor-core convolutions with hi/lo-split operands, fp32-class
+              accuracy) or 'plain' (strict fp32 cuDNN)
+Environment overrides: PIPS_B200_PRECISION, PIPS_B200_FEAT, PIPS_B200_FNET.
 """
 from __future__ import annotations
 
@@ -72,11 +74,12 @@ class DeltaBlock(nn.Module):
 
 
 @contextlib.contextmanager
-def _strict_fp32():
-    """fnet runs in true fp32: torch enables TF32 convolutions by default on Ampere+, which alone
-    moves trajectories by ~1e-2 px."""
+def _conv_math(allow_tf32: bool):
+    """Pin cuDNN's conv math for fnet.  torch enables plain TF32 convolutions by default on Ampere+, which
+    alone moves trajectories by ~1e-2 px (measured: fmaps error 2.5e-2); fnet therefore runs either in
+    strict fp32 ('plain') or in the 3xTF32 split mode ('x3', fp32-class accuracy on the tensor cores)."""
     c, m = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
         yield
@@ -86,7 +89,7 @@ def _strict_fp32():
 
 class Pips(nn.Module):
     def __init__(self, S=8, stride=8, *, precision: Optional[str] = None, feat_dtype: Optional[str] = None,
-                 max_seqs: int = 32768):
+                 fnet_mode: Optional[str] = None, max_seqs: int = 32768):
         super().__init__()
         self.S = S
         self.stride = stride
@@ -105,6 +108,9 @@ class Pips(nn.Module):
         feat_dtype = feat_dtype or os.environ.get("PIPS_B200_FEAT", "fp32")
         self._engine = RefineEngine(precision=precision, feat_dtype=feat_dtype, max_seqs=max_seqs)
         self._shard = None                      # (rank, world, group) when particle-sharded
+        self.fnet_mode = fnet_mode or os.environ.get("PIPS_B200_FNET", "x3")
+        if self.fnet_mode not in ("x3", "plain"):
+            raise ValueError("fnet_mode must be 'x3' (3xTF32 split convolutions) or 'plain' (strict fp32 cuDNN)")
 
     # ------------------------------------------------------------------ configuration
     @property
@@ -124,7 +130,10 @@ class Pips(nn.Module):
         """nets/pips.py:436-445: normalise to [-1,1], fnet per frame -> (B,S,128,H8,W8) fp32."""
         B, S, C, H, W = rgbs.shape
         x = 2 * (rgbs.float() / 255.0) - 1.0
-        with _strict_fp32():
+        # the split path detaches the weights: inference only (the training path keeps plain cuDNN + autograd)
+        x3 = self.fnet_mode == "x3" and x.is_cuda and not torch.is_grad_enabled()
+        self.fnet.mode = "x3" if x3 else "plain"
+        with _conv_math(allow_tf32=x3):
             fmaps = self.fnet(x.reshape(B * S, C, H, W))
         return fmaps.reshape(B, S, self.latent_dim, H // self.stride, W // self.stride)
 

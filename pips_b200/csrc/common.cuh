@@ -36,6 +36,28 @@ __device__ __forceinline__ float gelu_exact(float v) {
     return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
 }
 
+// GELU(x) = x * Phi(x) with Phi(-|x|) = 0.5 erfc(|x|/sqrt2) ~= 0.5 (a1 t + ... + a6 t^6) exp(-x^2/2),
+// t = 1/(1 + p |x|/sqrt2): a 6-term Abramowitz-Stegun-form fit (max error of the fit 7.8e-9, about
+// 4e-7 relative after fp32 evaluation -- the same class as an erff-based evaluation, ~12 instructions
+// instead of ~30 and branch-free).  Phi(x) for x > 0 is 1 - Phi(-x), so the negative tail has no
+// cancellation.  Used where GELU sits on a hot epilogue (FC1, token mixing).
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float u = fabsf(x) * 0.70710678118654752440f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.39032175941870945f, u, 1.0f)));
+    float poly = -0.22690528284688813f;
+    poly = fmaf(poly, t, 0.8816427529222105f);
+    poly = fmaf(poly, t, -0.6277422818132679f);
+    poly = fmaf(poly, t, 0.6443190264058088f);
+    poly = fmaf(poly, t, 0.09343682899024472f);
+    poly = fmaf(poly, t, 0.23524894852470762f);
+    poly *= t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * u * -1.4426950408889634f));
+    const float q = 0.5f * poly * e;                   // Phi(-|x|)
+    return x * (x > 0.0f ? 1.0f - q : q);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

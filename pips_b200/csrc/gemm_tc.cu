@@ -13,8 +13,8 @@
 //   warp 0      TMA producer   : cp.async.bulk.tensor 128B-swizzled K-chunks of A and W -> smem ring
 //   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (M=128,N=256,K=16) per chunk/term
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue       : tcgen05.ld the fp32 tile (one row per thread), bias / GELU(erf) /
-//                                residual / hi-lo split, vectorised stores
+//   warps 4..11 epilogue       : tcgen05.ld the fp32 tile (one row per thread, two warps per lane quadrant),
+//                                bias / GELU(erf) / residual / hi-lo split, vectorised stores
 // The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i
 // overlaps the MMAs of tile i+1.
 #include <cuda_bf16.h>
@@ -28,7 +28,7 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;                       // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;                 // 4 control warps + 8 epilogue warps
 constexpr uint32_t A_TILE_BYTES = BM * BK * 2;     // 16 KB
 constexpr uint32_t W_TILE_BYTES = BN * BK * 2;     // 32 KB
 
@@ -92,7 +92,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull0 + 8 * s, 1);
-            mbar_init(tempty0 + 8 * s, 128);
+            mbar_init(tempty0 + 8 * s, GEMM_THREADS - 128);
         }
         fence_barrier_init();
     }
@@ -165,25 +165,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         __syncwarp();
     } else if (warp >= 4) {
-        // ------------------------------------------------------------ epilogue (128 threads, one row each)
-        const int q = warp - 4;                                  // == warp % 4: TMEM lane quadrant
+        // ------------------------------------------------------------ epilogue (256 threads)
+        // Two warps per TMEM lane quadrant (a warp may only touch lanes 32*(warp%4)..+31); each takes half
+        // of the tile's 256 columns.  Thread = one output row; tcgen05.ld of the next 32-column chunk is
+        // in flight while the current one goes through bias / GELU / split / store.
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
             const int m0 = (t / tiles_n) * BM;
-            const int n0 = (t % tiles_n) * BN;
+            const int n0 = (t % tiles_n) * BN + half * (BN / 2);
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < args.M;
             mbar_wait(tfull0 + 8 * as, aphase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + c0, v);
-                tmem_ld_wait();
-                const int col = n0 + c0;
-                if (col >= args.N) continue;                     // warp-uniform
+            const uint32_t taddr = tmem_base + as * BN + half * (BN / 2) + (static_cast<uint32_t>(q * 32) << 16);
+
+            auto process = [&](const uint32_t (&v)[32], int col) {
+                if (col >= args.N) return;                       // warp-uniform
                 const bool full_chunk = col + 32 <= args.N;
                 float f[32];
 #pragma unroll
@@ -210,8 +210,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         uint32_t hw[4], lw[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const float g0 = gelu_exact(f[j + 2 * e]);
-                            const float g1 = gelu_exact(f[j + 2 * e + 1]);
+                            const float g0 = gelu_fast(f[j + 2 * e]);
+                            const float g1 = gelu_fast(f[j + 2 * e + 1]);
                             const __nv_bfloat16 h0 = __float2bfloat16_rn(g0), h1 = __float2bfloat16_rn(g1);
                             hw[e] = pack_bf16(h0, h1);
                             lw[e] = pack_bf16(__float2bfloat16_rn(g0 - __bfloat162float(h0)),
@@ -248,7 +248,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             if (col + j < args.N) po[j] = resid ? po[j] + f[j] : f[j];
                     }
                 }
-                __syncwarp();                                    // tcgen05.ld is warp-collective: reconverge
+            };
+
+            uint32_t va[32], vb[32];
+            tmem_ld_32x32(taddr, va);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN / 2; c0 += 64) {
+                tmem_ld_wait();
+                tmem_ld_32x32(taddr + c0 + 32, vb);
+                process(va, n0 + c0);
+                __syncwarp();                                    // tcgen05.ld / wait are warp-collective
+                tmem_ld_wait();
+                if (c0 + 64 < BN / 2) tmem_ld_32x32(taddr + c0 + 64, va);
+                process(vb, n0 + c0 + 32);
+                __syncwarp();
             }
             tc_fence_before();
             mbar_arrive(tempty0 + 8 * as);

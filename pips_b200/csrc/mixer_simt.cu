@@ -111,14 +111,18 @@ __device__ __forceinline__ void store_row4(const float (&v)[4], size_t off, __nv
 }
 
 // ------------------------------------------------------------------------------------------ token mixing
-__global__ void __launch_bounds__(TM_THREADS)
+__global__ void __launch_bounds__(TM_THREADS, 4)
 tokenmix_kernel(float* __restrict__ x, const float* __restrict__ ln1_w, const float* __restrict__ ln1_b,
                 const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                 const float* __restrict__ b2, const float* __restrict__ ln2_w, const float* __restrict__ ln2_b,
                 __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, float* y_f32) {
     __shared__ float red[4][8];
-    __shared__ float s_w1[32 * 8], s_b1[32], s_w2[8 * 32], s_b2[8];
-    for (int i = threadIdx.x; i < 256; i += TM_THREADS) { s_w1[i] = w1[i]; s_w2[i] = w2[i]; }
+    __shared__ __align__(16) float s_w1[32 * 8], s_w2t[32 * 8];   // w1[j][s] and w2 transposed to [j][s]
+    __shared__ float s_b1[32], s_b2[8];
+    for (int i = threadIdx.x; i < 256; i += TM_THREADS) {
+        s_w1[i] = w1[i];
+        s_w2t[(i & 31) * 8 + (i >> 5)] = w2[i];           // w2 is (8 s, 32 j)
+    }
     if (threadIdx.x < 32) s_b1[threadIdx.x] = b1[threadIdx.x];
     if (threadIdx.x < 8) s_b2[threadIdx.x] = b2[threadIdx.x];
 
@@ -141,23 +145,23 @@ tokenmix_kernel(float* __restrict__ x, const float* __restrict__ ln1_w, const fl
         for (int c = 0; c < 4; ++c) z[s][c] = s_b2[s];
 #pragma unroll 4
     for (int j = 0; j < 32; ++j) {
-        float h[4];
+        float h[4], wa[8], wb[8];
+        *reinterpret_cast<float4*>(wa) = *reinterpret_cast<const float4*>(s_w1 + j * 8);
+        *reinterpret_cast<float4*>(wa + 4) = *reinterpret_cast<const float4*>(s_w1 + j * 8 + 4);
+        *reinterpret_cast<float4*>(wb) = *reinterpret_cast<const float4*>(s_w2t + j * 8);
+        *reinterpret_cast<float4*>(wb + 4) = *reinterpret_cast<const float4*>(s_w2t + j * 8 + 4);
 #pragma unroll
         for (int c = 0; c < 4; ++c) h[c] = s_b1[j];
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            const float wv = s_w1[j * 8 + s];
+        for (int s = 0; s < 8; ++s)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) h[c] = fmaf(wv, yv[s][c], h[c]);
-        }
+            for (int c = 0; c < 4; ++c) h[c] = fmaf(wa[s], yv[s][c], h[c]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) h[c] = gelu_exact(h[c]);
+        for (int c = 0; c < 4; ++c) h[c] = gelu_fast(h[c]);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {
-            const float wv = s_w2[s * 32 + j];
+        for (int s = 0; s < 8; ++s)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) z[s][c] = fmaf(wv, h[c], z[s][c]);
-        }
+            for (int c = 0; c < 4; ++c) z[s][c] = fmaf(wb[s], h[c], z[s][c]);
     }
 #pragma unroll
     for (int s = 0; s < 8; ++s) {

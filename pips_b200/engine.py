@@ -7,6 +7,7 @@ memory and streams only.  The driver mirrors the state machine of ``Pips.forward
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -157,6 +158,8 @@ class RefineEngine:
         self._ws: Optional[Workspace] = None
         self._pyr: Optional[Pyramid] = None
         self._times = None
+        self._plans: Dict[tuple, "_GraphPlan"] = {}
+        self.use_graph = os.environ.get("PIPS_B200_GRAPH", "1") != "0"
         self.launches = 0                       # kernels launched by the last refine() call
 
     # ------------------------------------------------------------------ caches
@@ -167,6 +170,7 @@ class RefineEngine:
     def weights(self, module) -> PackedWeights:
         key = tuple((p.data_ptr(), p._version) for p in module.parameters())
         if self._weights is None or key != self._weights_key:
+            self._plans.clear()                                   # captured graphs point into the old pack
             self._weights = PackedWeights(module, self._stream())
             self._weights_key = key
         return self._weights
@@ -192,70 +196,100 @@ class RefineEngine:
         return self._times
 
     # ------------------------------------------------------------------ the loop
+    def _enqueue(self, lib, wc, pyr: Pyramid, ws: Workspace, fmaps2d, c, c0, ffeat, ffeats, feat_init, out, vis,
+                 B, S, nc, H8, W8, iters, stride, on_iter=None, build_pyramid=True) -> int:
+        """Enqueue every launch of one forward for ``nc`` particles on the current stream: pyramid, initial
+        features, ``iters`` refinement iterations, visibility head.  Returns the number of kernels launched."""
+        st = self._stream()
+        launches = 0
+        if build_pyramid:
+            pyr.build(fmaps2d, st)
+            launches += 4
+        c0.copy_(c)
+        if feat_init is None:
+            L.check(lib.pips_init_gather(L.ptr(pyr.f32[0]), B, S, nc, H8, W8, L.ptr(c), L.ptr(ffeat), L.ptr(ffeats), st),
+                    "pips_init_gather")
+            launches += 1
+        else:
+            ffeat.copy_(feat_init.reshape(B * nc, LATENT))
+            ffeats.copy_(ffeat.unsqueeze(1).expand(-1, S, -1))
+        lvl = pyr.levels()
+        prob = L.Problem()
+        prob.B, prob.S, prob.N, prob.H, prob.W = B, S, nc, H8, W8
+        prob.feat_dtype, prob.precision = self.feat_dtype, self.precision
+        for i in range(L.LEVELS):
+            prob.lvl[i] = L.ptr(lvl[i])
+        prob.times, prob.coords, prob.coords0, prob.ffeats = L.ptr(self.times(c.device)), L.ptr(c), L.ptr(c0), L.ptr(ffeats)
+        prob.stride = float(stride)
+        for it in range(iters):
+            L.check(lib.pips_refine_iter(C.byref(prob), C.byref(wc), C.byref(ws.c), L.ptr(out[it]), st), "pips_refine_iter")
+            launches += 1 + (1 + 3 * L.DEPTH + 2) + 1
+            if on_iter is not None:
+                on_iter(it, out[it])
+        L.check(lib.pips_vis_head(L.ptr(ffeats), wc.vis_w, wc.vis_b, L.ptr(vis), B, S, nc, st), "pips_vis_head")
+        return launches + 1
+
     def refine(self, module, fmaps: torch.Tensor, coords: torch.Tensor, feat_init: Optional[torch.Tensor],
                iters: int, stride: float, on_iter=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """fmaps (B,S,128,H8,W8) fp32, coords (B,S,N,2) fp32 in feature-map pixels.
         Returns preds (iters,B,S,N,2) in input pixels, vis_e (B,S,N) logits, ffeat (B,N,128).
-        ``on_iter(it, coords_px)`` (optional) is called right after iteration ``it`` has been enqueued,
-        when the particles fit one chunk -- the sharded path hangs its per-iteration all-gather there."""
+        ``on_iter(it, coords_px)`` (optional) is called once per iteration when the particles fit one
+        chunk -- the sharded path hangs its per-iteration all-gather there."""
         lib = L.load()
         B, S, Cc, H8, W8 = fmaps.shape
         if S != S_FRAMES or Cc != LATENT:
             raise L.PipsCudaError(f"pips_b200 CUDA path supports S=8, C=128 (got S={S}, C={Cc})")
         N = coords.shape[2]
         dev = fmaps.device
-        st = self._stream()
         w = self.weights(module)
-        pyr = self.pyramid(B * S, H8, W8, dev)
-        pyr.build(fmaps.reshape(B * S, Cc, H8, W8).contiguous(), st)
-        self.launches = 4
-        times = self.times(dev)
-        lvl = pyr.levels()
+        fmaps2d = fmaps.reshape(B * S, Cc, H8, W8).contiguous()
+        chunk = max(1, self.max_seqs // B)
 
+        if N <= chunk and self.use_graph and iters > 0:
+            plan = self._plan(w, B, S, N, H8, W8, iters, float(stride), feat_init is not None, dev)
+            preds, vis, ffeat = plan.run(fmaps2d, coords, feat_init)
+            self.launches = plan.launches
+            if on_iter is not None:
+                for it in range(iters):
+                    on_iter(it, preds[it])
+            return preds, vis, ffeat
+
+        pyr = self.pyramid(B * S, H8, W8, dev)
         preds = torch.empty(iters, B, S, N, 2, dtype=torch.float32, device=dev)
         vis = torch.empty(B, S, N, dtype=torch.float32, device=dev)
         ffeat_out = torch.empty(B, N, LATENT, dtype=torch.float32, device=dev)
-        chunk = max(1, self.max_seqs // B)
+        self.launches = 0
         for n0 in range(0, N, chunk):
             n1 = min(N, n0 + chunk)
             nc = n1 - n0
             whole = nc == N
-            c = coords if whole else coords[:, :, n0:n1]
-            c = c.contiguous().clone()
-            c0 = c.clone()
+            c = (coords if whole else coords[:, :, n0:n1]).contiguous().clone()
+            c0 = torch.empty_like(c)
             ffeat = torch.empty(B * nc, LATENT, dtype=torch.float32, device=dev)
             ffeats = torch.empty(B * nc, S, LATENT, dtype=torch.float32, device=dev)
-            if feat_init is None:
-                L.check(lib.pips_init_gather(L.ptr(pyr.f32[0]), B, S, nc, H8, W8, L.ptr(c), L.ptr(ffeat), L.ptr(ffeats), st),
-                        "pips_init_gather")
-                self.launches += 1
-            else:
-                fi = feat_init if whole else feat_init[:, n0:n1]
-                ffeat.copy_(fi.reshape(B * nc, LATENT))
-                ffeats.copy_(ffeat.unsqueeze(1).expand(-1, S, -1))
+            fi = None if feat_init is None else (feat_init if whole else feat_init[:, n0:n1])
             ws = self.workspace(B * nc, dev)
-            prob = L.Problem()
-            prob.B, prob.S, prob.N, prob.H, prob.W = B, S, nc, H8, W8
-            prob.feat_dtype, prob.precision = self.feat_dtype, self.precision
-            for i in range(L.LEVELS):
-                prob.lvl[i] = L.ptr(lvl[i])
-            prob.times, prob.coords, prob.coords0, prob.ffeats = L.ptr(times), L.ptr(c), L.ptr(c0), L.ptr(ffeats)
-            prob.stride = float(stride)
             out = preds if whole else torch.empty(iters, B, S, nc, 2, dtype=torch.float32, device=dev)
-            for it in range(iters):
-                L.check(lib.pips_refine_iter(C.byref(prob), C.byref(w.c), C.byref(ws.c), L.ptr(out[it]), st),
-                        "pips_refine_iter")
-                self.launches += 1 + (1 + 3 * L.DEPTH + 2) + 1
-                if on_iter is not None and whole:
-                    on_iter(it, out[it])
             v = vis if whole else torch.empty(B, S, nc, dtype=torch.float32, device=dev)
-            L.check(lib.pips_vis_head(L.ptr(ffeats), w.c.vis_w, w.c.vis_b, L.ptr(v), B, S, nc, st), "pips_vis_head")
-            self.launches += 1
+            self.launches += self._enqueue(lib, w.c, pyr, ws, fmaps2d, c, c0, ffeat, ffeats, fi, out, v, B, S, nc, H8, W8,
+                                           iters, stride, on_iter if whole else None, build_pyramid=(n0 == 0))
             if not whole:
                 preds[:, :, :, n0:n1] = out
                 vis[:, :, n0:n1] = v
             ffeat_out[:, n0:n1] = ffeat.reshape(B, nc, LATENT)
         return preds, vis, ffeat_out
+
+    def _plan(self, w: PackedWeights, B, S, N, H8, W8, iters, stride, has_feat, dev) -> "_GraphPlan":
+        key = (id(w), B, S, N, H8, W8, iters, stride, has_feat, str(dev))
+        plan = self._plans.get(key)
+        if plan is None:
+            while len(self._plans) >= 2:                          # each plan owns a full workspace
+                self._plans.pop(next(iter(self._plans)))
+            plan = _GraphPlan(self, w, B, S, N, H8, W8, iters, stride, has_feat, dev)
+            self._plans[key] = plan
+        else:
+            self._plans[key] = self._plans.pop(key)               # LRU order
+        return plan
 
     # ------------------------------------------------------------------ instrumentation
     def profile_iteration(self, module, fmaps: torch.Tensor, coords: torch.Tensor, stride: float, reps: int = 3):
@@ -325,3 +359,50 @@ class RefineEngine:
                                                     L.ptr(out), float(stride), B, S, N, st))
         torch.cuda.synchronize()
         return {k: [a.elapsed_time(b) for a, b in v] for k, v in rec.items()}, dict(B=B, S=S, N=N, M=M)
+
+
+class _GraphPlan:
+    """One captured CUDA graph of a whole forward (pyramid .. vis head) for a fixed problem signature,
+    with its own static buffers; replayed with new inputs copied in.  ~250 launches per forward collapse
+    into one graph launch, which is what matters for small problems (demo / chained windows)."""
+
+    def __init__(self, eng: RefineEngine, w: PackedWeights, B, S, N, H8, W8, iters, stride, has_feat, dev):
+        lib = L.load()
+        self.w = w
+        self.iters = iters
+        self.pyr = Pyramid(B * S, H8, W8, eng.feat_dtype, dev)
+        self.ws = Workspace(B * N, eng.precision, dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.fmaps = torch.zeros(B * S, LATENT, H8, W8, **f32)
+        self.c = torch.zeros(B, S, N, 2, **f32)
+        self.c0 = torch.zeros_like(self.c)
+        self.feat_in = torch.zeros(B, N, LATENT, **f32) if has_feat else None
+        self.ffeat = torch.zeros(B * N, LATENT, **f32)
+        self.ffeats = torch.zeros(B * N, S, LATENT, **f32)
+        self.preds = torch.zeros(iters, B, S, N, 2, **f32)
+        self.vis = torch.zeros(B, S, N, **f32)
+        self.shape = (B, N)
+        eng.times(dev)
+
+        def enqueue():
+            return eng._enqueue(lib, w.c, self.pyr, self.ws, self.fmaps, self.c, self.c0, self.ffeat, self.ffeats,
+                                self.feat_in, self.preds, self.vis, B, S, N, H8, W8, iters, stride)
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self.launches = enqueue()                 # eager warm-up: function attributes, lazy module load
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            enqueue()
+
+    def run(self, fmaps2d, coords, feat_init):
+        B, N = self.shape
+        self.fmaps.copy_(fmaps2d)
+        self.c.copy_(coords)
+        if self.feat_in is not None:
+            self.feat_in.copy_(feat_init)
+        self.graph.replay()
+        return self.preds.clone(), self.vis.clone(), self.ffeat.reshape(B, N, LATENT).clone()

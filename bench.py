@@ -84,6 +84,35 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads() -> int:
+    """Threads for the CPU legs: the cores this process may actually use (affinity and cgroup quota), then a
+    short calibration over power-of-two counts -- oversubscribing a quota-limited container is slower."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    cands = sorted({c for c in (n, 64, 32, 16, 8) if 1 <= c <= n})
+    if len(cands) == 1:
+        return cands[0]
+    a = torch.randn(8, 64, 96, 128)
+    w = torch.randn(64, 64, 3, 3)
+    m = torch.randn(2048, 512)
+    best, best_t = cands[-1], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        torch.nn.functional.conv2d(a, w, padding=1); m @ m.t()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.nn.functional.conv2d(a, w, padding=1); m @ m.t()
+        dt = time.perf_counter() - t0
+        if dt < best_t * 0.95:
+            best, best_t = c, dt
+    return best
+
+
 def make_inputs(n_global: int):
     from oracle import pips_oracle as po          # input generator + weights only (not on the measured path)
     rgbs = po.smooth_video(B, S, H, W, seed=1234).to(torch.bfloat16)       # integers 0..255: exact in bf16
@@ -100,7 +129,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import pips_oracle as po
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
     sd, rgbs, xys = make_inputs(N_PER_GPU)
     bs, ns = 1, 256                                # reference-style chunk (test_on_davis.py:111-125 chunks N by 256)
@@ -128,13 +157,13 @@ def run_reference(args, rank, world):
             "config": {"workload": f"cfg2 sample: {sample}", "stride": STRIDE},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ our arm
 def cpu_baseline_leg():
     from oracle import pips_oracle as po
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
     sd, rgbs, xys = make_inputs(N_PER_GPU)
     bs, ns = 1, 256
@@ -265,10 +294,26 @@ def run_ours(args, rank, world, local_rank):
             "whole_path_tensor_frac": (updates * UNIT_FLOP / (t_dev / args.steps)) / 1e12 / pk["bf16_tflops_sustained"] / world}
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line goes to the real stdout; everything else (NCCL banners, warnings) was rerouted."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                                  # libraries that print to fd 1 (NCCL version banner) -> stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -51,6 +51,9 @@ const char* pips_last_error(void);
  * non-NULL, receive the same values rounded to bf16. */
 int pips_pyramid_build(const float* fmaps_nchw, int frames, int H, int W,
                        float* const* lvl_f32, void* const* lvl_bf16, void* stream);
+/* same, for feature maps that are already channels-last (B*S, H, W, 128) -- what the fused encoder path emits */
+int pips_pyramid_build_nhwc(const float* fmaps_nhwc, int frames, int H, int W,
+                            float* const* lvl_f32, void* const* lvl_bf16, void* stream);
 
 /* utils/samp.py:5-78 via nets/pips.py:463-466: bilinear gather of frame 0 at the query (indices
  * clamped, weights not), broadcast over S.  coords is the full (B,S,N,2) state (frame 0 is read). */
@@ -97,6 +100,18 @@ int pips_vis_head(const float* ffeats, const float* w, const float* b, float* vi
 
 /* v -> (hi, lo) bf16 with hi = rn(v), lo = rn(v - hi); lo may be NULL.  Used to pack weights. */
 int pips_split_bf16(const float* src, void* hi, void* lo, size_t n, void* stream);
+
+/* ---- channels-last element-wise stages of fnet (BasicEncoder, nets/pips.py:131-281; upstream of the loop) ----
+ * InstanceNorm2d statistics of y (N, HW, C) NHWC: stats = [N][2][C] (mean, rstd); partial is [N][chunks][2][C] scratch. */
+int pips_inorm_stats(const float* y, int N, int HW, int C, float* partial, int chunks, float* stats, void* stream);
+/* out = relu_out?( relu_main?( norm(y) ) + norm?(r) ); written as plain fp32 and/or as the [hi|lo|hi] TF32 split
+ * (3*C channels at row stride split_ld) that conv2d_3xtf32 consumes.  stats_y / r / stats_r may be NULL. */
+int pips_inorm_apply(const float* y, const float* stats_y, const float* r, const float* stats_r, int relu_main, int relu_out,
+                     float* out_plain, float* out_split, int split_ld, int N, int HW, int C, void* stream);
+/* F.interpolate(bilinear, align_corners=True) (nets/pips.py:269-272) of src (N,Hs,Ws,C) into channels
+ * [c_off, c_off+C) of the split concat dst (N,Ho,Wo,3*Ctot). */
+int pips_resize_split3(const float* src, int N, int Hs, int Ws, int C, float* dst, int Ho, int Wo, int Ctot, int c_off,
+                       void* stream);
 
 /* Whole-iteration operator: everything between `for itr in range(iters)` and the append of
  * coords*stride (nets/pips.py:499-539, minus the dead fcp heat-map :504-511). */

@@ -58,6 +58,7 @@ _SIGNATURES = {
     "pips_abi_version": (_i, []),
     "pips_last_error": (C.c_char_p, []),
     "pips_pyramid_build": (_i, [_p, _i, _i, _i, C.POINTER(_p), C.POINTER(_p), _p]),
+    "pips_pyramid_build_nhwc": (_i, [_p, _i, _i, _i, C.POINTER(_p), C.POINTER(_p), _p]),
     "pips_init_gather": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "pips_corr_gather": (_i, [C.POINTER(_p), _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p]),
     "pips_gemm_tc": (_i, [_p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _i, _p]),
@@ -67,6 +68,9 @@ _SIGNATURES = {
     "pips_update": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _p]),
     "pips_vis_head": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "pips_split_bf16": (_i, [_p, _p, _p, C.c_size_t, _p]),
+    "pips_inorm_stats": (_i, [_p, _i, _i, _i, _p, _i, _p, _p]),
+    "pips_inorm_apply": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _p]),
+    "pips_resize_split3": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _p]),
     "pips_mixer_forward": (_i, [C.POINTER(Weights), C.POINTER(Workspace), _i, _i, _p]),
     "pips_refine_iter": (_i, [C.POINTER(Problem), C.POINTER(Weights), C.POINTER(Workspace), _p, _p]),
 }

@@ -54,6 +54,14 @@ __global__ void avgpool2_nhwc_kernel(const float* __restrict__ in, float* __rest
     }
 }
 
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n4) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(in)[i];
+        reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16(__float2bfloat16_rn(v.x), __float2bfloat16_rn(v.y)),
+                                                      pack_bf16(__float2bfloat16_rn(v.z), __float2bfloat16_rn(v.w)));
+    }
+}
+
 // one warp per (b, n): 4 clamped taps x 128 channels, unclamped weights, result broadcast to the S rows
 __global__ void init_gather_kernel(const float* __restrict__ lvl0, int B, int S, int N, int H, int W,
                                    const float* __restrict__ coords, float* __restrict__ ffeat, float* __restrict__ ffeats) {
@@ -90,17 +98,31 @@ __global__ void init_gather_kernel(const float* __restrict__ lvl0, int B, int S,
 
 using namespace pips;
 
-extern "C" int pips_pyramid_build(const float* fmaps_nchw, int frames, int H, int W, float* const* lvl_f32,
-                                  void* const* lvl_bf16, void* stream) {
-    if (!fmaps_nchw || !lvl_f32) return fail("pips_pyramid_build: null pointer");
+static int pyramid_common(const float* fmaps, bool nhwc, int frames, int H, int W, float* const* lvl_f32,
+                          void* const* lvl_bf16, void* stream) {
+    if (!fmaps || !lvl_f32) return fail("pips_pyramid_build: null pointer");
     if (frames <= 0 || H < 8 || W < 8) return fail("pips_pyramid_build: need frames > 0 and H, W >= 8 (4 pooled levels)");
     for (int l = 0; l < PIPS_LEVELS; ++l)
         if (!lvl_f32[l] || (lvl_bf16 && !lvl_bf16[l])) return fail("pips_pyramid_build: null level pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int HW = H * W;
-    dim3 grid((HW + 31) / 32, 4, frames), block(32, 8);
-    nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(fmaps_nchw, lvl_f32[0], lvl_bf16 ? static_cast<__nv_bfloat16*>(lvl_bf16[0]) : nullptr, HW);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    if (nhwc) {
+        const size_t n = static_cast<size_t>(frames) * HW * 128;
+        if (fmaps != lvl_f32[0]) {
+            e = cudaMemcpyAsync(lvl_f32[0], fmaps, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return fail_cuda("pips_pyramid_build: level 0 copy", e);
+        }
+        if (lvl_bf16) {
+            size_t blocks = (n / 4 + 255) / 256;
+            if (blocks > 148 * 8) blocks = 148 * 8;
+            f32_to_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(fmaps, static_cast<__nv_bfloat16*>(lvl_bf16[0]), n / 4);
+        }
+    } else {
+        dim3 grid((HW + 31) / 32, 4, frames), block(32, 8);
+        nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(fmaps, lvl_f32[0], lvl_bf16 ? static_cast<__nv_bfloat16*>(lvl_bf16[0]) : nullptr, HW);
+    }
+    e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda("pips_pyramid_build: level 0", e);
     int hi = H, wi = W;
     for (int l = 1; l < PIPS_LEVELS; ++l) {
@@ -115,6 +137,16 @@ extern "C" int pips_pyramid_build(const float* fmaps_nchw, int frames, int H, in
         hi = ho; wi = wo;
     }
     return 0;
+}
+
+extern "C" int pips_pyramid_build(const float* fmaps_nchw, int frames, int H, int W, float* const* lvl_f32,
+                                  void* const* lvl_bf16, void* stream) {
+    return pyramid_common(fmaps_nchw, false, frames, H, W, lvl_f32, lvl_bf16, stream);
+}
+
+extern "C" int pips_pyramid_build_nhwc(const float* fmaps_nhwc, int frames, int H, int W, float* const* lvl_f32,
+                                       void* const* lvl_bf16, void* stream) {
+    return pyramid_common(fmaps_nhwc, true, frames, H, W, lvl_f32, lvl_bf16, stream);
 }
 
 extern "C" int pips_init_gather(const float* lvl0_f32, int B, int S, int N, int H, int W, const float* coords, float* ffeat,

@@ -1,0 +1,109 @@
+"""Channels-last inference path of the feature encoder.
+
+Same arithmetic as ``Encoder.forward`` in 'x3' mode (cuDNN TF32 tensor-core convolutions over
+[hi | lo | hi] split operands => fp32-class accuracy), but every activation stays NHWC and the
+element-wise work between two convolutions -- InstanceNorm, ReLU, residual add, TF32 split, bilinear
+resize into the 416-channel concat -- runs in three fused kernels of libpips_b200
+(csrc/encoder_ops.cu) instead of ~14 eager passes per convolution.  The result is returned
+channels-last, which is already the layout of pyramid level 0.
+
+Reference semantics: BasicEncoder.forward nets/pips.py:247-281, ResidualBlock.forward :173-181.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib as L
+from .encoder import Encoder, _tf32_hi
+
+
+def _st() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _w3(conv: torch.nn.Conv2d, pad_in_to: int = 0) -> torch.Tensor:
+    """[w_hi | w_hi | w_lo] along the input channels, channels-last, cached per weight version."""
+    w = conv.weight
+    key = (w.data_ptr(), w._version, pad_in_to)
+    if getattr(conv, "_w3cl_key", None) != key:
+        wd = w.detach().float()
+        if pad_in_to and wd.shape[1] < pad_in_to:
+            wd = F.pad(wd, (0, 0, 0, 0, 0, pad_in_to - wd.shape[1]))
+        hi = _tf32_hi(wd)
+        conv._w3cl = torch.cat([hi, hi, wd - hi], dim=1).contiguous(memory_format=torch.channels_last)
+        conv._w3cl_key = key
+    return conv._w3cl
+
+
+def _conv(x3_nhwc: torch.Tensor, conv: torch.nn.Conv2d, pad_in_to: int = 0) -> torch.Tensor:
+    """x3_nhwc (N,H,W,3C) -> conv output as an (N,Ho,Wo,Cout) contiguous NHWC tensor."""
+    y = F.conv2d(x3_nhwc.permute(0, 3, 1, 2), _w3(conv, pad_in_to), conv.bias, conv.stride, conv.padding)
+    y = y.permute(0, 2, 3, 1)
+    return y if y.is_contiguous() else y.contiguous()
+
+
+class _Ops:
+    def __init__(self, device):
+        self.lib = L.load()
+        self.dev = device
+
+    def stats(self, y: torch.Tensor) -> torch.Tensor:
+        N, H, W, C = y.shape
+        hw = H * W
+        chunks = max(1, min(16, hw // 64))
+        partial = torch.empty(N, chunks, 2, C, dtype=torch.float32, device=self.dev)
+        st = torch.empty(N, 2, C, dtype=torch.float32, device=self.dev)
+        L.check(self.lib.pips_inorm_stats(L.ptr(y), N, hw, C, L.ptr(partial), chunks, L.ptr(st), _st()), "pips_inorm_stats")
+        return st
+
+    def apply(self, y, stats, r=None, stats_r=None, relu_main=True, relu_out=False, plain=False, split=True):
+        N, H, W, C = y.shape
+        out_p = torch.empty_like(y) if plain else None
+        out_s = torch.empty(N, H, W, 3 * C, dtype=torch.float32, device=self.dev) if split else None
+        L.check(self.lib.pips_inorm_apply(L.ptr(y), L.ptr(stats), L.ptr(r), L.ptr(stats_r), int(relu_main), int(relu_out),
+                                          L.ptr(out_p), L.ptr(out_s), 3 * C, N, H * W, C, _st()), "pips_inorm_apply")
+        return out_p, out_s
+
+    def resize_into(self, src, dst3, c_off, ctot):
+        N, Hs, Ws, C = src.shape
+        _, Ho, Wo, _ = dst3.shape
+        L.check(self.lib.pips_resize_split3(L.ptr(src), N, Hs, Ws, C, L.ptr(dst3), Ho, Wo, ctot, c_off, _st()),
+                "pips_resize_split3")
+
+
+def fnet_fast(enc: Encoder, x: torch.Tensor) -> torch.Tensor:
+    """x (N,3,H,W) fp32 in [-1,1] on CUDA -> feature maps (N, H//stride, W//stride, 128) NHWC fp32.
+    Requires torch.backends.cudnn.allow_tf32 = True (set by Pips.encode)."""
+    assert x.is_cuda and x.dtype == torch.float32
+    ops = _Ops(x.device)
+    N, _, H, W = x.shape
+    H8, W8 = H // enc.stride, W // enc.stride
+
+    # stem: 3 -> 64, 7x7 / 2.  Input channels padded 3 -> 4 per split block (cuDNN NHWC kernels want C % 4 == 0).
+    xh = _tf32_hi(x)
+    z = torch.zeros(N, 1, H, W, dtype=torch.float32, device=x.device)
+    x12 = torch.cat([xh, z, x - xh, z, xh, z], dim=1).permute(0, 2, 3, 1).contiguous()
+    y = _conv(x12, enc.conv1, pad_in_to=4)
+    X, X3 = ops.apply(y, ops.stats(y), relu_main=True, plain=True, split=True)
+
+    ctot = 64 + 96 + 128 + 128
+    cat3 = torch.empty(N, H8, W8, 3 * ctot, dtype=torch.float32, device=x.device)
+    c_off = 0
+    for i in range(1, 5):
+        for blk in getattr(enc, f"layer{i}"):
+            y1 = _conv(X3, blk.conv1)
+            _, A3 = ops.apply(y1, ops.stats(y1), relu_main=True)
+            y2 = _conv(A3, blk.conv2)
+            s2 = ops.stats(y2)
+            if blk.downsample is not None:
+                d = _conv(X3, blk.downsample[0])
+                X, X3 = ops.apply(y2, s2, r=d, stats_r=ops.stats(d), relu_main=True, relu_out=True, plain=True)
+            else:
+                X, X3 = ops.apply(y2, s2, r=X, relu_main=True, relu_out=True, plain=True)
+        ops.resize_into(X, cat3, c_off, ctot)
+        c_off += X.shape[-1]
+
+    y = _conv(cat3, enc.conv2)
+    _, A3 = ops.apply(y, ops.stats(y), relu_main=True)
+    return _conv(A3, enc.conv3)

@@ -136,10 +136,16 @@ class Pyramid:
         return self.bf16 if self.feat_dtype == L.FEAT_BF16 else self.f32
 
     def build(self, fmaps: torch.Tensor, stream) -> None:
+        """fmaps: (frames,128,H,W) fp32, either NCHW-contiguous or channels-last (NHWC memory)."""
         lib = L.load()
-        assert fmaps.dtype == torch.float32 and fmaps.is_contiguous()
-        L.check(lib.pips_pyramid_build(L.ptr(fmaps), self.frames, self.H, self.W, self.f32_ptrs,
-                                       self.bf16_ptrs, stream), "pips_pyramid_build")
+        assert fmaps.dtype == torch.float32
+        if fmaps.is_contiguous():
+            L.check(lib.pips_pyramid_build(L.ptr(fmaps), self.frames, self.H, self.W, self.f32_ptrs,
+                                           self.bf16_ptrs, stream), "pips_pyramid_build")
+        else:
+            assert fmaps.permute(0, 2, 3, 1).is_contiguous(), "fmaps must be NCHW- or NHWC-contiguous"
+            L.check(lib.pips_pyramid_build_nhwc(L.ptr(fmaps), self.frames, self.H, self.W, self.f32_ptrs,
+                                                self.bf16_ptrs, stream), "pips_pyramid_build_nhwc")
 
 
 class RefineEngine:
@@ -242,11 +248,14 @@ class RefineEngine:
         N = coords.shape[2]
         dev = fmaps.device
         w = self.weights(module)
-        fmaps2d = fmaps.reshape(B * S, Cc, H8, W8).contiguous()
+        fmaps2d = fmaps.reshape(B * S, Cc, H8, W8)                  # a view for both NCHW and channels-last inputs
+        if not fmaps2d.is_contiguous() and not fmaps2d.permute(0, 2, 3, 1).is_contiguous():
+            fmaps2d = fmaps2d.contiguous()
         chunk = max(1, self.max_seqs // B)
 
         if N <= chunk and self.use_graph and iters > 0:
-            plan = self._plan(w, B, S, N, H8, W8, iters, float(stride), feat_init is not None, dev)
+            plan = self._plan(w, B, S, N, H8, W8, iters, float(stride), feat_init is not None, dev,
+                              nhwc=not fmaps2d.is_contiguous())
             preds, vis, ffeat = plan.run(fmaps2d, coords, feat_init)
             self.launches = plan.launches
             if on_iter is not None:
@@ -279,13 +288,13 @@ class RefineEngine:
             ffeat_out[:, n0:n1] = ffeat.reshape(B, nc, LATENT)
         return preds, vis, ffeat_out
 
-    def _plan(self, w: PackedWeights, B, S, N, H8, W8, iters, stride, has_feat, dev) -> "_GraphPlan":
-        key = (id(w), B, S, N, H8, W8, iters, stride, has_feat, str(dev))
+    def _plan(self, w: PackedWeights, B, S, N, H8, W8, iters, stride, has_feat, dev, nhwc=False) -> "_GraphPlan":
+        key = (id(w), B, S, N, H8, W8, iters, stride, has_feat, str(dev), nhwc)
         plan = self._plans.get(key)
         if plan is None:
             while len(self._plans) >= 2:                          # each plan owns a full workspace
                 self._plans.pop(next(iter(self._plans)))
-            plan = _GraphPlan(self, w, B, S, N, H8, W8, iters, stride, has_feat, dev)
+            plan = _GraphPlan(self, w, B, S, N, H8, W8, iters, stride, has_feat, dev, nhwc)
             self._plans[key] = plan
         else:
             self._plans[key] = self._plans.pop(key)               # LRU order
@@ -366,14 +375,15 @@ class _GraphPlan:
     with its own static buffers; replayed with new inputs copied in.  ~250 launches per forward collapse
     into one graph launch, which is what matters for small problems (demo / chained windows)."""
 
-    def __init__(self, eng: RefineEngine, w: PackedWeights, B, S, N, H8, W8, iters, stride, has_feat, dev):
+    def __init__(self, eng: RefineEngine, w: PackedWeights, B, S, N, H8, W8, iters, stride, has_feat, dev, nhwc=False):
         lib = L.load()
         self.w = w
         self.iters = iters
         self.pyr = Pyramid(B * S, H8, W8, eng.feat_dtype, dev)
         self.ws = Workspace(B * N, eng.precision, dev)
         f32 = dict(dtype=torch.float32, device=dev)
-        self.fmaps = torch.zeros(B * S, LATENT, H8, W8, **f32)
+        self.fmaps_nchw = torch.zeros(B * S, LATENT, H8, W8, **f32)
+        self.fmaps_nhwc = self.fmaps_nchw.view(B * S, H8, W8, LATENT).permute(0, 3, 1, 2)   # same storage, NHWC strides
         self.c = torch.zeros(B, S, N, 2, **f32)
         self.c0 = torch.zeros_like(self.c)
         self.feat_in = torch.zeros(B, N, LATENT, **f32) if has_feat else None
@@ -384,9 +394,11 @@ class _GraphPlan:
         self.shape = (B, N)
         eng.times(dev)
 
+        self.nhwc = nhwc
+
         def enqueue():
-            return eng._enqueue(lib, w.c, self.pyr, self.ws, self.fmaps, self.c, self.c0, self.ffeat, self.ffeats,
-                                self.feat_in, self.preds, self.vis, B, S, N, H8, W8, iters, stride)
+            return eng._enqueue(lib, w.c, self.pyr, self.ws, self.fmaps_nhwc if nhwc else self.fmaps_nchw, self.c, self.c0,
+                                self.ffeat, self.ffeats, self.feat_in, self.preds, self.vis, B, S, N, H8, W8, iters, stride)
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -400,7 +412,7 @@ class _GraphPlan:
 
     def run(self, fmaps2d, coords, feat_init):
         B, N = self.shape
-        self.fmaps.copy_(fmaps2d)
+        (self.fmaps_nhwc if self.nhwc else self.fmaps_nchw).copy_(fmaps2d)
         self.c.copy_(coords)
         if self.feat_in is not None:
             self.feat_in.copy_(feat_init)

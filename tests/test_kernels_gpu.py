@@ -48,6 +48,25 @@ def test_pyramid_build(H, W):
         assert torch.equal(bf[l].cpu(), r.to(torch.bfloat16))
 
 
+def test_pyramid_build_nhwc_input():
+    lib = L.load()
+    torch.manual_seed(2)
+    fmaps = torch.randn(1, 8, 128, 23, 37)
+    ref = po.build_pyramid(fmaps)
+    src = fmaps[0].permute(0, 2, 3, 1).contiguous().to(DEV)          # (8, H, W, 128)
+    f32, bf = [], []
+    h, w = 23, 37
+    for _ in range(4):
+        f32.append(torch.empty(8, h, w, 128, device=DEV))
+        bf.append(torch.empty(8, h, w, 128, device=DEV, dtype=torch.bfloat16))
+        h, w = h // 2, w // 2
+    L.check(lib.pips_pyramid_build_nhwc(L.ptr(src), 8, 23, 37, L.ptr_array(f32), L.ptr_array(bf), _st()))
+    _sync_check()
+    for l in range(4):
+        r = ref[l][0].permute(0, 2, 3, 1).contiguous()
+        assert torch.equal(f32[l].cpu(), r) and torch.equal(bf[l].cpu(), r.to(torch.bfloat16))
+
+
 def test_init_gather_clamps_indices():
     lib = L.load()
     torch.manual_seed(1)

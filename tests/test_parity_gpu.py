@@ -85,6 +85,30 @@ def test_strict_fp32_fnet_mode():
     assert np.abs(torch.stack(preds).cpu().numpy() - GOLD["tiny_s8/preds"]).max() < 1e-4
 
 
+@pytest.mark.parametrize("H,W,stride", [(128, 160, 8), (184, 360, 8), (96, 128, 4)])
+def test_fnet_modes_agree(H, W, stride):
+    """'fast' (channels-last, fused element-wise kernels, 3xTF32 convs) and 'x3' against strict-fp32 cuDNN."""
+    sd = po.init_state_dict(seed=3)
+    rgbs = po.smooth_video(1, 8, H, W, seed=77).to(DEV)
+    outs = {}
+    for mode in ("plain", "x3", "fast"):
+        model = Pips(S=8, stride=stride, fnet_mode=mode).to(DEV).eval()
+        model.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            outs[mode] = model.encode(rgbs).contiguous()
+        assert outs[mode].shape == (1, 8, 128, H // stride, W // stride)
+    scale = outs["plain"].abs().max().item()
+    for mode in ("x3", "fast"):
+        err = (outs[mode] - outs["plain"]).abs().max().item()
+        print(f"fnet {mode} vs plain: max|err| {err:.3e} (|fmaps| max {scale:.2f})")
+        assert err < 1e-3
+    with torch.no_grad():
+        ref = po.fnet(sd, (2 * (rgbs.cpu() / 255.0) - 1.0).reshape(8, 3, H, W), stride)
+    err = (outs["fast"].cpu().reshape(8, 128, H // stride, W // stride) - ref).abs().max().item()
+    print(f"fnet fast vs CPU oracle: max|err| {err:.3e}")
+    assert err < 1e-3
+
+
 def test_graph_replay_equals_eager():
     c = CASES["rect_s4_oob"]
     sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])

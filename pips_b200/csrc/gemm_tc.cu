@@ -17,17 +17,14 @@
 //                                bias / GELU(erf) / residual / hi-lo split, vectorised stores
 // The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i
 // overlaps the MMAs of tile i+1.
-#include <cuda_bf16.h>
+#include <stdlib.h>
 
-#include "common.cuh"
-#include "ptx.cuh"
+#include "gemm_common.cuh"
 
 namespace pips {
 
 constexpr int BM = 128;
 constexpr int BN = 256;
-constexpr int BK = 64;                       // 64 bf16 = one 128-byte swizzle row
-constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 384;                 // 4 control warps + 8 epilogue warps
 constexpr uint32_t A_TILE_BYTES = BM * BK * 2;     // 16 KB
 constexpr uint32_t W_TILE_BYTES = BN * BK * 2;     // 32 KB
@@ -38,17 +35,6 @@ struct GemmCfg {
     static constexpr uint32_t kStageBytes = kOperandCopies * (A_TILE_BYTES + W_TILE_BYTES);
     static constexpr int kStages = TERMS == 3 ? 2 : 4;
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-};
-
-struct GemmArgs {
-    int M, N, K;                 // valid rows / cols, K multiple of 64
-    const float* bias;           // [N]
-    int epilogue;                // PIPS_EPI_*
-    float* out_f32;              // BIAS / BIAS_RESID target (row stride ldo)
-    int ldo;
-    __nv_bfloat16* out_hi;       // BIAS_GELU target (row stride ldh); out_lo may be null
-    __nv_bfloat16* out_lo;
-    int ldh;
 };
 
 template <int TERMS>
@@ -182,85 +168,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             tc_fence_after();
             const uint32_t taddr = tmem_base + as * BN + half * (BN / 2) + (static_cast<uint32_t>(q * 32) << 16);
 
-            auto process = [&](const uint32_t (&v)[32], int col) {
-                if (col >= args.N) return;                       // warp-uniform
-                const bool full_chunk = col + 32 <= args.N;
-                float f[32];
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 b;
-                    if (full_chunk) {
-                        b = __ldg(reinterpret_cast<const float4*>(args.bias + col + j));
-                    } else {
-                        b.x = col + j + 0 < args.N ? __ldg(args.bias + col + j + 0) : 0.f;
-                        b.y = col + j + 1 < args.N ? __ldg(args.bias + col + j + 1) : 0.f;
-                        b.z = col + j + 2 < args.N ? __ldg(args.bias + col + j + 2) : 0.f;
-                        b.w = col + j + 3 < args.N ? __ldg(args.bias + col + j + 3) : 0.f;
-                    }
-                    f[j + 0] = __uint_as_float(v[j + 0]) + b.x;
-                    f[j + 1] = __uint_as_float(v[j + 1]) + b.y;
-                    f[j + 2] = __uint_as_float(v[j + 2]) + b.z;
-                    f[j + 3] = __uint_as_float(v[j + 3]) + b.w;
-                }
-                if (row_ok && args.epilogue == PIPS_EPI_BIAS_GELU) {
-                    __nv_bfloat16* ph = args.out_hi + static_cast<size_t>(row) * args.ldh + col;
-                    __nv_bfloat16* pl = args.out_lo ? args.out_lo + static_cast<size_t>(row) * args.ldh + col : nullptr;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint32_t hw[4], lw[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float g0 = gelu_fast(f[j + 2 * e]);
-                            const float g1 = gelu_fast(f[j + 2 * e + 1]);
-                            const __nv_bfloat16 h0 = __float2bfloat16_rn(g0), h1 = __float2bfloat16_rn(g1);
-                            hw[e] = pack_bf16(h0, h1);
-                            lw[e] = pack_bf16(__float2bfloat16_rn(g0 - __bfloat162float(h0)),
-                                              __float2bfloat16_rn(g1 - __bfloat162float(h1)));
-                        }
-                        if (full_chunk) {
-                            *reinterpret_cast<uint4*>(ph + j) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                            if (pl) *reinterpret_cast<uint4*>(pl + j) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-                        } else {
-                            for (int e = 0; e < 8; ++e) {
-                                if (col + j + e < args.N) {
-                                    const uint32_t hh = hw[e >> 1], ll = lw[e >> 1];
-                                    reinterpret_cast<uint16_t*>(ph)[j + e] = (e & 1) ? (hh >> 16) : (hh & 0xffff);
-                                    if (pl) reinterpret_cast<uint16_t*>(pl)[j + e] = (e & 1) ? (ll >> 16) : (ll & 0xffff);
-                                }
-                            }
-                        }
-                    }
-                } else if (row_ok) {
-                    float* po = args.out_f32 + static_cast<size_t>(row) * args.ldo + col;
-                    const bool resid = args.epilogue == PIPS_EPI_BIAS_RESID;
-                    if (full_chunk) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 o = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                            if (resid) {
-                                const float4 r = *reinterpret_cast<const float4*>(po + j);
-                                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                            }
-                            *reinterpret_cast<float4*>(po + j) = o;
-                        }
-                    } else {
-                        for (int j = 0; j < 32; ++j)
-                            if (col + j < args.N) po[j] = resid ? po[j] + f[j] : f[j];
-                    }
-                }
-            };
-
             uint32_t va[32], vb[32];
             tmem_ld_32x32(taddr, va);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN / 2; c0 += 64) {
                 tmem_ld_wait();
                 tmem_ld_32x32(taddr + c0 + 32, vb);
-                process(va, n0 + c0);
+                epilogue_chunk(args, va, row, row_ok, n0 + c0);
                 __syncwarp();                                    // tcgen05.ld / wait are warp-collective
                 tmem_ld_wait();
                 if (c0 + 64 < BN / 2) tmem_ld_32x32(taddr + c0 + 64, va);
-                process(vb, n0 + c0 + 32);
+                epilogue_chunk(args, vb, row, row_ok, n0 + c0 + 32);
                 __syncwarp();
             }
             tc_fence_before();
@@ -283,6 +201,18 @@ static bool make_operand_map(CUtensorMap* map, const void* ptr, int rows, int K,
     cuuint32_t estr[2] = {1, 1};
     return encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int gemm_tc_pair_dispatch(const void* a_hi, const void* a_lo, int lda, int a_rows, const void* w_hi, const void* w_lo, int ldw,
+                          int w_rows, const GemmArgs& args, cudaStream_t st);       // gemm_tc2.cu
+
+static bool use_pair_kernel() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PIPS_B200_GEMM_PAIR");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 
 }  // namespace pips
@@ -308,6 +238,14 @@ extern "C" int pips_gemm_tc(const void* a_hi, const void* a_lo, int lda, int a_r
     } else {
         return fail("pips_gemm_tc: unknown epilogue");
     }
+    GemmArgs args;
+    args.M = M; args.N = N; args.K = K; args.bias = bias; args.epilogue = epilogue;
+    args.out_f32 = out_f32; args.ldo = ldo;
+    args.out_hi = static_cast<__nv_bfloat16*>(out_hi); args.out_lo = static_cast<__nv_bfloat16*>(out_lo); args.ldh = ldh;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // CTA-pair kernel (cta_group::2) whenever the allocations cover whole 256-row pair tiles
+    if (use_pair_kernel() && M > 128 && (a_rows % 256) == 0 && (w_rows % 256) == 0)
+        return gemm_tc_pair_dispatch(a_hi, x3 ? a_lo : nullptr, lda, a_rows, w_hi, x3 ? w_lo : nullptr, ldw, w_rows, args, st);
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     if (!make_operand_map(&ma_hi, a_hi, a_rows, K, lda, BM)) return fail("pips_gemm_tc: tensor map (A hi) failed");
     if (!make_operand_map(&mw_hi, w_hi, w_rows, K, ldw, BN)) return fail("pips_gemm_tc: tensor map (W hi) failed");
@@ -317,13 +255,8 @@ extern "C" int pips_gemm_tc(const void* a_hi, const void* a_lo, int lda, int a_r
         if (!make_operand_map(&ma_lo, a_lo, a_rows, K, lda, BM)) return fail("pips_gemm_tc: tensor map (A lo) failed");
         if (!make_operand_map(&mw_lo, w_lo, w_rows, K, ldw, BN)) return fail("pips_gemm_tc: tensor map (W lo) failed");
     }
-    GemmArgs args;
-    args.M = M; args.N = N; args.K = K; args.bias = bias; args.epilogue = epilogue;
-    args.out_f32 = out_f32; args.ldo = ldo;
-    args.out_hi = static_cast<__nv_bfloat16*>(out_hi); args.out_lo = static_cast<__nv_bfloat16*>(out_lo); args.ldh = ldh;
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
     if (x3) {
         static bool attr = false;

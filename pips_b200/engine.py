@@ -90,8 +90,8 @@ class Workspace:
 
     def __init__(self, seqs: int, precision: int, device):
         self.seqs = seqs
-        rows = _round_up(seqs * S_FRAMES, 128)
-        sq = _round_up(seqs, 128)
+        rows = _round_up(seqs * S_FRAMES, 256)        # whole 256-row CTA-pair tiles
+        sq = _round_up(seqs, 256)
         self.c = L.Workspace()
         self.c.rows_alloc, self.c.seqs_alloc = rows, sq
         self.keep: Dict[str, torch.Tensor] = {}

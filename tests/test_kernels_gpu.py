@@ -177,6 +177,7 @@ def _split(t):
     return hi, lo
 
 
+@pytest.mark.parametrize("pair", [False, True])
 @pytest.mark.parametrize("terms", [3, 1])
 @pytest.mark.parametrize("M,N,K,epi", [
     (128, 256, 64, L.EPI_BIAS),            # one tile, one K block
@@ -187,10 +188,15 @@ def _split(t):
     (300, 1040, 512, L.EPI_BIAS),          # head: partial N tile
     (40000, 512, 512, L.EPI_BIAS_RESID),   # > 148 tiles: persistent loop + TMEM double buffering
 ])
-def test_gemm_tc(terms, M, N, K, epi):
+def test_gemm_tc(terms, M, N, K, epi, pair):
+    """pair=True: allocations cover whole 256-row tiles -> the cta_group::2 kernel; False -> single-CTA kernel."""
     lib = L.load()
     torch.manual_seed(7)
     Ma, Na = (M + 127) // 128 * 128, (N + 255) // 256 * 256
+    if pair:
+        Ma = (M + 255) // 256 * 256
+    elif Ma % 256 == 0:
+        Ma += 128
     a = torch.zeros(Ma, K)
     a[:M] = torch.randn(M, K)
     w = torch.zeros(Na, K)

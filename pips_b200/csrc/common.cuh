@@ -42,19 +42,18 @@ __device__ __forceinline__ float gelu_exact(float v) {
 // instead of ~30 and branch-free).  Phi(x) for x > 0 is 1 - Phi(-x), so the negative tail has no
 // cancellation.  Used where GELU sits on a hot epilogue (FC1, token mixing).
 __device__ __forceinline__ float gelu_fast(float x) {
-    const float u = fabsf(x) * 0.70710678118654752440f;
+    // constants folded: t = 1/(1 + (p/sqrt2)|x|), coefficients pre-multiplied by 0.5, exponent -(x^2/2) log2(e)
     float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.39032175941870945f, u, 1.0f)));
-    float poly = -0.22690528284688813f;
-    poly = fmaf(poly, t, 0.8816427529222105f);
-    poly = fmaf(poly, t, -0.6277422818132679f);
-    poly = fmaf(poly, t, 0.6443190264058088f);
-    poly = fmaf(poly, t, 0.09343682899024472f);
-    poly = fmaf(poly, t, 0.23524894852470762f);
-    poly *= t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.27599915312530316f, fabsf(x), 1.0f)));
+    float q = -0.11345264142344407f;
+    q = fmaf(q, t, 0.44082137646110525f);
+    q = fmaf(q, t, -0.31387114090663395f);
+    q = fmaf(q, t, 0.3221595132029044f);
+    q = fmaf(q, t, 0.04671841449512236f);
+    q = fmaf(q, t, 0.11762447426235381f);
     float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * u * -1.4426950408889634f));
-    const float q = 0.5f * poly * e;                   // Phi(-|x|)
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.7213475204444817f));
+    q = q * t * e;                                     // Phi(-|x|)
     return x * (x > 0.0f ? 1.0f - q : q);
 }
 

@@ -34,7 +34,7 @@ struct GemmCfg {
     static constexpr int kOperandCopies = TERMS == 3 ? 2 : 1;             // hi (+ lo)
     static constexpr uint32_t kStageBytes = kOperandCopies * (A_TILE_BYTES + W_TILE_BYTES);
     static constexpr int kStages = TERMS == 3 ? 2 : 4;
-    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 template <int TERMS>
@@ -47,7 +47,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle atoms need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint8_t* epi_stage = smem + kStages * Cfg::kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES);
     // barrier layout: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
     const uint32_t full0 = smem_u32(bars);
     const uint32_t empty0 = full0 + 8 * kStages;
@@ -91,6 +92,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Register budget per warpgroup: the control warps (0-3) need few, the epilogue warpgroups (4-7, 8-11) many.
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
@@ -150,35 +154,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
         // ------------------------------------------------------------ epilogue (256 threads)
         // Two warps per TMEM lane quadrant (a warp may only touch lanes 32*(warp%4)..+31); each takes half
         // of the tile's 256 columns.  Thread = one output row; tcgen05.ld of the next 32-column chunk is
         // in flight while the current one goes through bias / GELU / split / store.
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
+        uint8_t* my_stage = epi_stage + (warp - 4) * 4096;
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
             const int m0 = (t / tiles_n) * BM;
             const int n0 = (t % tiles_n) * BN + half * (BN / 2);
-            const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < args.M;
+            const int row0 = m0 + q * 32;
             mbar_wait(tfull0 + 8 * as, aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + as * BN + half * (BN / 2) + (static_cast<uint32_t>(q * 32) << 16);
 
             uint32_t va[32], vb[32];
+            float bias[32];
             tmem_ld_32x32(taddr, va);
+            load_bias_chunk(args, n0, bias);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN / 2; c0 += 64) {
                 tmem_ld_wait();
                 tmem_ld_32x32(taddr + c0 + 32, vb);
-                epilogue_chunk(args, va, row, row_ok, n0 + c0);
+                epilogue_chunk(args, va, bias, row0, n0 + c0, n0 + c0 + 32, my_stage);
                 __syncwarp();                                    // tcgen05.ld / wait are warp-collective
                 tmem_ld_wait();
                 if (c0 + 64 < BN / 2) tmem_ld_32x32(taddr + c0 + 64, va);
-                epilogue_chunk(args, vb, row, row_ok, n0 + c0 + 32);
+                epilogue_chunk(args, vb, bias, row0, n0 + c0 + 32, c0 + 64 < BN / 2 ? n0 + c0 + 64 : -1, my_stage);
                 __syncwarp();
             }
             tc_fence_before();

@@ -28,7 +28,7 @@ struct PairCfg {
     static constexpr int kCopies = TERMS == 3 ? 2 : 1;
     static constexpr uint32_t kStageBytes = kCopies * (P_A_BYTES + P_W_BYTES);      // per CTA: 64 KB / 32 KB
     static constexpr int kStages = TERMS == 3 ? 3 : 6;
-    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256;
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + EPI_STAGE_BYTES + 1024 + 256;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -88,7 +88,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     constexpr int kStages = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint8_t* epi_stage = smem + kStages * Cfg::kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES);
     const uint32_t full0 = smem_u32(bars);                 // used in the leader only
     const uint32_t empty0 = full0 + 8 * kStages;           // per CTA
     const uint32_t tfull0 = empty0 + 8 * kStages;          // per CTA
@@ -134,6 +135,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Register budget per warpgroup: the control warps (0-3) need few, the epilogue warpgroups (4-7, 8-11) many.
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
         if (lane == 0) {
@@ -194,31 +198,35 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
         // ------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
+        uint8_t* my_stage = epi_stage + (warp - 4) * 4096;
         int it = 0;
         for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
             const uint32_t as = it & 1, aphase = (it >> 1) & 1;
             const int m0 = (t / tiles_n) * P_BM + static_cast<int>(rank) * 128;
             const int n0 = (t % tiles_n) * P_BN + half * (P_BN / 2);
-            const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < args.M;
+            const int row0 = m0 + q * 32;
             mbar_wait(tfull0 + 8 * as, aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + as * P_BN + half * (P_BN / 2) + (static_cast<uint32_t>(q * 32) << 16);
             uint32_t va[32], vb[32];
+            float bias[32];
             tmem_ld_32x32(taddr, va);
+            load_bias_chunk(args, n0, bias);
 #pragma unroll 1
             for (int c0 = 0; c0 < P_BN / 2; c0 += 64) {
                 tmem_ld_wait();
                 tmem_ld_32x32(taddr + c0 + 32, vb);
-                epilogue_chunk(args, va, row, row_ok, n0 + c0);
-                __syncwarp();
+                epilogue_chunk(args, va, bias, row0, n0 + c0, n0 + c0 + 32, my_stage);
+                __syncwarp();                                    // tcgen05.ld / wait are warp-collective
                 tmem_ld_wait();
                 if (c0 + 64 < P_BN / 2) tmem_ld_32x32(taddr + c0 + 64, va);
-                epilogue_chunk(args, vb, row, row_ok, n0 + c0 + 32);
+                epilogue_chunk(args, vb, bias, row0, n0 + c0 + 32, c0 + 64 < P_BN / 2 ? n0 + c0 + 64 : -1, my_stage);
                 __syncwarp();
             }
             tc_fence_before();

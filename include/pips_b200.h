@@ -58,14 +58,18 @@ int pips_pyramid_build_nhwc(const float* fmaps_nhwc, int frames, int H, int W,
 /* utils/samp.py:5-78 via nets/pips.py:463-466: bilinear gather of frame 0 at the query (indices
  * clamped, weights not), broadcast over S.  coords is the full (B,S,N,2) state (frame 0 is read). */
 int pips_init_gather(const float* lvl0_f32, int B, int S, int N, int H, int W, const float* coords,
+                     const int* frame_base /* NULL or [B*N] */, int frames_per_batch,
                      float* ffeat /* (B*N,128) */, float* ffeats /* (B*N,S,128) */, void* stream);
 
 /* nets/pips.py:502,:513 (CorrBlock.corr + .sample) fused with the layout glue :517-522 and
  * utils/misc.py:44-69 (get_3d_embedding): writes the 519-wide mixer input row
  *   [ ffeat 128 | corr 4x49 | sin/cos(flow_x) 64 | (flow_y) 64 | (t) 64 | flow_x flow_y t | 0-pad to 576 ]
- * for every (b,n,s) without materialising the all-pairs volume.  Any of x_hi/x_lo/x_f32 may be NULL. */
+ * for every (b,n,s) without materialising the all-pairs volume.  Any of x_hi/x_lo/x_f32 may be NULL.
+ * Chained long-video tracking (chain_demo.py:40-83): when frame_base is non-NULL the pyramid holds
+ * frames_per_batch (T) frames per batch element and track (b,n) reads frames min(frame_base[b*N+n] + s, T-1). */
 int pips_corr_gather(const void* const* lvl, int feat_dtype, int B, int S, int N, int H, int W,
                      const float* coords, const float* ffeats, const float* times /* [S] */,
+                     const int* frame_base /* NULL or [B*N] */, int frames_per_batch,
                      void* x_hi, void* x_lo, float* x_f32, int ldx, void* stream);
 
 /* nn.Linear on tensor cores: out = epi(A[M,K] . W[N,K]^T + bias).  a_lo/w_lo NULL => plain bf16. */
@@ -154,6 +158,8 @@ typedef struct pips_problem {
     const float* coords0;                 /* (B,S,N,2) initial coords (frame 0 is re-locked)           */
     float* ffeats;                        /* (B*N,S,128) in/out                                        */
     float stride;
+    const int* frame_base;                /* NULL, or [B*N] window starts for chained tracking         */
+    int frames_per_batch;                 /* frames per batch element in the pyramid when frame_base   */
 } pips_problem;
 
 /* DeltaBlock.forward on prepared input rows (nets/pips.py:304-311, mixer :111-123): x0 -> ws->delta */

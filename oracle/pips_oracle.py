@@ -420,3 +420,40 @@ def forward(sd: SD, xys: Tensor, rgbs: Tensor, iters: int = 3, stride: int = 8,
     if return_feat:
         return preds, preds2, vis_e, ffeat, None
     return preds, preds2, vis_e, None
+
+
+def chain_track(forward_fn, rgbs: Tensor, xy0: Tensor, iters: int = 6):
+    """chain_demo.py:40-83 (run_model's per-particle loop; test_on_badja.py:65-113 is the same logic).
+    ``forward_fn(xys (1,1,2), rgb_seq (1,8,3,H,W), feat_init) -> (preds, vis_e, ffeat)`` is one 8-frame
+    model call with return_feat=True.  rgbs (1,T,3,H,W), xy0 (1,N,2) -> trajs (1,T,N,2), skips per particle."""
+    B, T = rgbs.shape[:2]
+    N = xy0.shape[1]
+    trajs = torch.zeros(B, T, N, 2, dtype=torch.float32)
+    skips = []
+    for n in range(N):
+        cur, done, feat_init = 0, False, None
+        traj = torch.zeros(B, T, 2, dtype=torch.float32)
+        traj[:, 0] = xy0[:, n]
+        hist = []
+        while not done:
+            end = cur + 8
+            seq = rgbs[:, cur:end]
+            s_local = seq.shape[1]
+            seq = torch.cat([seq, seq[:, -1].unsqueeze(1).repeat(1, 8 - s_local, 1, 1, 1)], dim=1)    # :50-52
+            preds, vis, feat_init = forward_fn(traj[:, cur].reshape(1, -1, 2), seq, feat_init)      # :54-57
+            vis = torch.sigmoid(vis)                                                                  # :59
+            traj[:, cur:end] = preds[-1].reshape(1, 8, 2)[:, :s_local]                                # :60-61
+            thr, si = 0.9, 7
+            while True:                                                                               # :63-76
+                if vis[0, si] > thr:
+                    break
+                si -= 1
+                if si == 1:
+                    thr -= 0.02
+                    si = 7
+            hist.append(si)
+            cur += si                                                                                 # :79
+            done = cur >= T
+        trajs[:, :, n] = traj
+        skips.append(hist)
+    return trajs, skips

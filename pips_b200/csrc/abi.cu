@@ -138,7 +138,7 @@ extern "C" int pips_refine_iter(const pips_problem* p, const pips_weights* w, co
     const int seqs = p->B * p->N;
     const bool f32 = p->precision == PIPS_PREC_F32;
     const bool x3 = p->precision == PIPS_PREC_BF16X3;
-    int rc = pips_corr_gather(p->lvl, p->feat_dtype, p->B, p->S, p->N, p->H, p->W, p->coords, p->ffeats, p->times,
+    int rc = pips_corr_gather(p->lvl, p->feat_dtype, p->B, p->S, p->N, p->H, p->W, p->coords, p->ffeats, p->times, p->frame_base, p->frames_per_batch,
                               f32 ? nullptr : ws->x0_hi, x3 ? ws->x0_lo : nullptr, f32 ? ws->x0_f32 : nullptr,
                               PIPS_KITCHEN_PAD, stream);
     if (rc) return rc;

@@ -40,6 +40,8 @@ struct CgArgs {
     const float* coords;     // (B,S,N,2)
     const float* ffeats;     // (B*N,S,128)
     const float* times;      // [S]
+    const int* frame_base;   // optional [B*N]: window start of each track inside its clip of T frames (chained tracking)
+    int T;                   // frames per batch element in the pyramid (== S when frame_base is null)
     __nv_bfloat16* x_hi;
     __nv_bfloat16* x_lo;
     float* x_f32;
@@ -72,7 +74,9 @@ __device__ __forceinline__ UnitInfo load_unit(const CgArgs& a, long long u, long
         const long long seq = u / a.S;
         const int b = static_cast<int>(seq / a.N), n = static_cast<int>(seq % a.N);
         const float2 c = *reinterpret_cast<const float2*>(a.coords + ((static_cast<size_t>(b) * a.S + s) * a.N + n) * 2);
-        ui.cx = c.x; ui.cy = c.y; ui.frame = b * a.S + s;
+        ui.cx = c.x; ui.cy = c.y;
+        // chained windows replicate the clip's last frame past its end (chain_demo.py:50-52)
+        ui.frame = a.frame_base ? b * a.T + min(a.frame_base[seq] + s, a.T - 1) : b * a.S + s;
     }
     return ui;
 }
@@ -283,8 +287,8 @@ static int launch_corr_gather(const void* const* lvl, CUtensorMapDataType dt, co
 using namespace pips;
 
 extern "C" int pips_corr_gather(const void* const* lvl, int feat_dtype, int B, int S, int N, int H, int W, const float* coords,
-                                const float* ffeats, const float* times, void* x_hi, void* x_lo, float* x_f32, int ldx,
-                                void* stream) {
+                                const float* ffeats, const float* times, const int* frame_base, int frames_per_batch,
+                                void* x_hi, void* x_lo, float* x_f32, int ldx, void* stream) {
     if (!lvl || !coords || !ffeats || !times) return fail("pips_corr_gather: null pointer");
     if (S != PIPS_S) return fail("pips_corr_gather: S must be 8");
     if (B <= 0 || N <= 0) return fail("pips_corr_gather: empty problem");
@@ -299,10 +303,12 @@ extern "C" int pips_corr_gather(const void* const* lvl, int feat_dtype, int B, i
         if (!lvl[l]) return fail("pips_corr_gather: null level pointer");
         a.H[l] = h; a.W[l] = w; h /= 2; w /= 2;
     }
+    if (frame_base && frames_per_batch <= 0) return fail("pips_corr_gather: frame_base needs frames_per_batch > 0");
     a.coords = coords; a.ffeats = ffeats; a.times = times;
+    a.frame_base = frame_base; a.T = frame_base ? frames_per_batch : S;
     a.x_hi = static_cast<__nv_bfloat16*>(x_hi); a.x_lo = static_cast<__nv_bfloat16*>(x_lo); a.x_f32 = x_f32; a.ldx = ldx;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (feat_dtype == PIPS_FEAT_F32) return launch_corr_gather<float>(lvl, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a, B * S, st);
-    if (feat_dtype == PIPS_FEAT_BF16) return launch_corr_gather<__nv_bfloat16>(lvl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a, B * S, st);
+    if (feat_dtype == PIPS_FEAT_F32) return launch_corr_gather<float>(lvl, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a, B * a.T, st);
+    if (feat_dtype == PIPS_FEAT_BF16) return launch_corr_gather<__nv_bfloat16>(lvl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a, B * a.T, st);
     return fail("pips_corr_gather: unknown feat_dtype");
 }

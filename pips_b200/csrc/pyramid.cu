@@ -64,7 +64,8 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* 
 
 // one warp per (b, n): 4 clamped taps x 128 channels, unclamped weights, result broadcast to the S rows
 __global__ void init_gather_kernel(const float* __restrict__ lvl0, int B, int S, int N, int H, int W,
-                                   const float* __restrict__ coords, float* __restrict__ ffeat, float* __restrict__ ffeats) {
+                                   const float* __restrict__ coords, const int* __restrict__ frame_base, int T,
+                                   float* __restrict__ ffeat, float* __restrict__ ffeats) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B * N) return;
     const int b = warp / N, n = warp % N;
@@ -79,7 +80,8 @@ __global__ void init_gather_kernel(const float* __restrict__ lvl0, int B, int S,
     const int y1 = static_cast<int>(fminf(fmaxf(y1f, 0.f), static_cast<float>(H - 1)));
     const float w00 = (x1f - x) * (y1f - y), w01 = (x - x0f) * (y1f - y);
     const float w10 = (x1f - x) * (y - y0f), w11 = (x - x0f) * (y - y0f);
-    const float* img = lvl0 + static_cast<size_t>(b) * S * H * W * 128;          // frame (b, s=0)
+    const int frame = frame_base ? b * T + min(frame_base[warp], T - 1) : b * S;  // first frame of the track's window
+    const float* img = lvl0 + static_cast<size_t>(frame) * H * W * 128;
     const float4 a = *reinterpret_cast<const float4*>(img + (static_cast<size_t>(y0) * W + x0) * 128 + lane * 4);
     const float4 bq = *reinterpret_cast<const float4*>(img + (static_cast<size_t>(y0) * W + x1) * 128 + lane * 4);
     const float4 c = *reinterpret_cast<const float4*>(img + (static_cast<size_t>(y1) * W + x0) * 128 + lane * 4);
@@ -149,12 +151,12 @@ extern "C" int pips_pyramid_build_nhwc(const float* fmaps_nhwc, int frames, int 
     return pyramid_common(fmaps_nhwc, true, frames, H, W, lvl_f32, lvl_bf16, stream);
 }
 
-extern "C" int pips_init_gather(const float* lvl0_f32, int B, int S, int N, int H, int W, const float* coords, float* ffeat,
-                                float* ffeats, void* stream) {
+extern "C" int pips_init_gather(const float* lvl0_f32, int B, int S, int N, int H, int W, const float* coords,
+                                const int* frame_base, int frames_per_batch, float* ffeat, float* ffeats, void* stream) {
     if (!lvl0_f32 || !coords || !ffeat || !ffeats) return fail("pips_init_gather: null pointer");
     if (B <= 0 || N <= 0 || S <= 0) return fail("pips_init_gather: empty problem");
     const int warps = B * N;
-    init_gather_kernel<<<(warps * 32 + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(lvl0_f32, B, S, N, H, W, coords, ffeat, ffeats);
+    init_gather_kernel<<<(warps * 32 + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(lvl0_f32, B, S, N, H, W, coords, frame_base, frames_per_batch, ffeat, ffeats);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail_cuda("pips_init_gather", e);
 }

@@ -165,6 +165,7 @@ class RefineEngine:
         self._pyr: Optional[Pyramid] = None
         self._times = None
         self._plans: Dict[tuple, "_GraphPlan"] = {}
+        self._pyramid_is_current = False        # set by callers that reuse one pyramid over many refine() calls
         self.use_graph = os.environ.get("PIPS_B200_GRAPH", "1") != "0"
         self.launches = 0                       # kernels launched by the last refine() call
 
@@ -203,7 +204,7 @@ class RefineEngine:
 
     # ------------------------------------------------------------------ the loop
     def _enqueue(self, lib, wc, pyr: Pyramid, ws: Workspace, fmaps2d, c, c0, ffeat, ffeats, feat_init, out, vis,
-                 B, S, nc, H8, W8, iters, stride, on_iter=None, build_pyramid=True) -> int:
+                 B, S, nc, H8, W8, iters, stride, on_iter=None, build_pyramid=True, frame_base=None, T=0) -> int:
         """Enqueue every launch of one forward for ``nc`` particles on the current stream: pyramid, initial
         features, ``iters`` refinement iterations, visibility head.  Returns the number of kernels launched."""
         st = self._stream()
@@ -213,8 +214,8 @@ class RefineEngine:
             launches += 4
         c0.copy_(c)
         if feat_init is None:
-            L.check(lib.pips_init_gather(L.ptr(pyr.f32[0]), B, S, nc, H8, W8, L.ptr(c), L.ptr(ffeat), L.ptr(ffeats), st),
-                    "pips_init_gather")
+            L.check(lib.pips_init_gather(L.ptr(pyr.f32[0]), B, S, nc, H8, W8, L.ptr(c), L.ptr(frame_base), T, L.ptr(ffeat),
+                                         L.ptr(ffeats), st), "pips_init_gather")
             launches += 1
         else:
             ffeat.copy_(feat_init.reshape(B * nc, LATENT))
@@ -227,6 +228,7 @@ class RefineEngine:
             prob.lvl[i] = L.ptr(lvl[i])
         prob.times, prob.coords, prob.coords0, prob.ffeats = L.ptr(self.times(c.device)), L.ptr(c), L.ptr(c0), L.ptr(ffeats)
         prob.stride = float(stride)
+        prob.frame_base, prob.frames_per_batch = L.ptr(frame_base), T
         for it in range(iters):
             L.check(lib.pips_refine_iter(C.byref(prob), C.byref(wc), C.byref(ws.c), L.ptr(out[it]), st), "pips_refine_iter")
             launches += 1 + (1 + 3 * L.DEPTH + 2) + 1
@@ -236,24 +238,30 @@ class RefineEngine:
         return launches + 1
 
     def refine(self, module, fmaps: torch.Tensor, coords: torch.Tensor, feat_init: Optional[torch.Tensor],
-               iters: int, stride: float, on_iter=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+               iters: int, stride: float, on_iter=None, frame_base: Optional[torch.Tensor] = None
+               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """fmaps (B,S,128,H8,W8) fp32, coords (B,S,N,2) fp32 in feature-map pixels.
         Returns preds (iters,B,S,N,2) in input pixels, vis_e (B,S,N) logits, ffeat (B,N,128).
         ``on_iter(it, coords_px)`` (optional) is called once per iteration when the particles fit one
-        chunk -- the sharded path hangs its per-iteration all-gather there."""
+        chunk -- the sharded path hangs its per-iteration all-gather there.
+        ``frame_base`` (B,N) int32 (optional): chained tracking -- fmaps then holds T >= 1 frames per batch
+        element and track (b,n) works on frames min(frame_base[b,n] + s, T-1), s = 0..7."""
         lib = L.load()
-        B, S, Cc, H8, W8 = fmaps.shape
-        if S != S_FRAMES or Cc != LATENT:
-            raise L.PipsCudaError(f"pips_b200 CUDA path supports S=8, C=128 (got S={S}, C={Cc})")
+        B, T, Cc, H8, W8 = fmaps.shape
+        S = coords.shape[1]
+        if S != S_FRAMES or Cc != LATENT or (frame_base is None and T != S):
+            raise L.PipsCudaError(f"pips_b200 CUDA path supports S=8, C=128 (got S={S}, T={T}, C={Cc})")
+        if frame_base is not None:
+            frame_base = frame_base.to(device=fmaps.device, dtype=torch.int32).contiguous()
         N = coords.shape[2]
         dev = fmaps.device
         w = self.weights(module)
-        fmaps2d = fmaps.reshape(B * S, Cc, H8, W8)                  # a view for both NCHW and channels-last inputs
+        fmaps2d = fmaps.reshape(B * T, Cc, H8, W8)                  # a view for both NCHW and channels-last inputs
         if not fmaps2d.is_contiguous() and not fmaps2d.permute(0, 2, 3, 1).is_contiguous():
             fmaps2d = fmaps2d.contiguous()
         chunk = max(1, self.max_seqs // B)
 
-        if N <= chunk and self.use_graph and iters > 0:
+        if N <= chunk and self.use_graph and iters > 0 and frame_base is None:
             plan = self._plan(w, B, S, N, H8, W8, iters, float(stride), feat_init is not None, dev,
                               nhwc=not fmaps2d.is_contiguous())
             preds, vis, ffeat = plan.run(fmaps2d, coords, feat_init)
@@ -263,7 +271,7 @@ class RefineEngine:
                     on_iter(it, preds[it])
             return preds, vis, ffeat
 
-        pyr = self.pyramid(B * S, H8, W8, dev)
+        pyr = self.pyramid(B * T, H8, W8, dev)
         preds = torch.empty(iters, B, S, N, 2, dtype=torch.float32, device=dev)
         vis = torch.empty(B, S, N, dtype=torch.float32, device=dev)
         ffeat_out = torch.empty(B, N, LATENT, dtype=torch.float32, device=dev)
@@ -280,8 +288,10 @@ class RefineEngine:
             ws = self.workspace(B * nc, dev)
             out = preds if whole else torch.empty(iters, B, S, nc, 2, dtype=torch.float32, device=dev)
             v = vis if whole else torch.empty(B, S, nc, dtype=torch.float32, device=dev)
+            fb = None if frame_base is None else (frame_base if whole else frame_base[:, n0:n1].contiguous())
             self.launches += self._enqueue(lib, w.c, pyr, ws, fmaps2d, c, c0, ffeat, ffeats, fi, out, v, B, S, nc, H8, W8,
-                                           iters, stride, on_iter if whole else None, build_pyramid=(n0 == 0))
+                                           iters, stride, on_iter if whole else None,
+                                           build_pyramid=(n0 == 0 and not self._pyramid_is_current), frame_base=fb, T=T)
             if not whole:
                 preds[:, :, :, n0:n1] = out
                 vis[:, :, n0:n1] = v
@@ -321,7 +331,7 @@ class RefineEngine:
         c0 = c.clone()
         ffeat = torch.empty(B * N, LATENT, dtype=torch.float32, device=dev)
         ffeats = torch.empty(B * N, S, LATENT, dtype=torch.float32, device=dev)
-        L.check(lib.pips_init_gather(L.ptr(pyr.f32[0]), B, S, N, H8, W8, L.ptr(c), L.ptr(ffeat), L.ptr(ffeats), st))
+        L.check(lib.pips_init_gather(L.ptr(pyr.f32[0]), B, S, N, H8, W8, L.ptr(c), None, 0, L.ptr(ffeat), L.ptr(ffeats), st))
         ws = self.workspace(B * N, dev).c
         times = self.times(dev)
         out = torch.empty(B, S, N, 2, dtype=torch.float32, device=dev)
@@ -347,7 +357,7 @@ class RefineEngine:
 
         for _ in range(reps):
             timed("corr_gather", lambda: lib.pips_corr_gather(
-                lvl, self.feat_dtype, B, S, N, H8, W8, L.ptr(c), L.ptr(ffeats), L.ptr(times),
+                lvl, self.feat_dtype, B, S, N, H8, W8, L.ptr(c), L.ptr(ffeats), L.ptr(times), None, 0,
                 None if f32 else ws.x0_hi, ws.x0_lo if x3 else None, ws.x0_f32 if f32 else None, L.KPAD, st))
             dense("gemm_in", (ws.x0_hi, ws.x0_lo, ws.x0_f32), L.KPAD, ws.rows_alloc, (w.in_w_hi, w.in_w_lo, w.in_w_f32), L.KPAD,
                   L.DIM, M, L.DIM, L.KPAD, w.in_b, L.EPI_BIAS, ws.x, L.DIM, (None, None, None), 0)

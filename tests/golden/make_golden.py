@@ -43,6 +43,15 @@ def loss_targets(c, xys):
     return trajs_g, vis_g, valids
 
 
+CHAIN_CASE = dict(T=19, H=96, W=128, N=5, stride=4, iters=6, head_scale=0.05, seed=7)
+
+
+def chain_inputs(c):
+    rgbs = po.smooth_video(1, c["T"], c["H"], c["W"], seed=500 + c["seed"])
+    xy0 = po.random_queries(1, c["N"], c["H"], c["W"], seed=600 + c["seed"])
+    return rgbs, xy0
+
+
 def case_inputs(c):
     """Shared with tests/: deterministic inputs for a golden case."""
     rgbs = po.smooth_video(c["B"], 8, c["H"], c["W"], seed=100 + c["seed"])
@@ -97,6 +106,22 @@ def main():
         out[name + "/vis_e"] = vis_e.numpy()
         out[name + "/losses"] = np.array([float(l) for l in losses], dtype=np.float64)
         print(name, "losses", out[name + "/losses"])
+    # chained long-video tracking (chain_demo.py:40-83) with the reference model as the 8-frame tracker
+    c = CHAIN_CASE
+    sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+    model = Pips(S=8, stride=c["stride"]).eval()
+    model.load_state_dict(sd, strict=True)
+    rgbs, xy0 = chain_inputs(c)
+
+    def ref_window(xys, seq, feat_init):
+        with torch.no_grad():
+            o = model(xys, seq, iters=c["iters"], feat_init=feat_init, return_feat=True)
+        return o[0], o[2], o[3]
+
+    trajs, skips = po.chain_track(ref_window, rgbs, xy0, iters=c["iters"])
+    out["chain/trajs"] = trajs.numpy()
+    out["chain/skips"] = np.array([len(h) for h in skips] + [s for h in skips for s in h], dtype=np.int64)
+    print("chain skips", skips)
     np.savez_compressed(os.path.join(HERE, "reference_outputs.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_outputs.npz"))
 

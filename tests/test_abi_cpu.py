@@ -25,7 +25,7 @@ def test_argument_validation_without_gpu():
     lib = L.load()
     assert lib.pips_gemm_tc(0, 0, 512, 128, 0, 0, 512, 256, 128, 256, 100, 0, 0, 0, 0, 0, 0, 0, 0) != 0
     assert b"multiple of 64" in lib.pips_last_error()
-    assert lib.pips_corr_gather(None, 0, 1, 7, 1, 16, 16, 0, 0, 0, 0, 0, 0, 576, 0) != 0
+    assert lib.pips_corr_gather(None, 0, 1, 7, 1, 16, 16, 0, 0, 0, None, 0, 0, 0, 0, 576, 0) != 0
     assert lib.pips_refine_iter(None, None, None, 0, 0) != 0
 
 

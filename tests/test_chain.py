@@ -1,0 +1,79 @@
+"""Chained long-video tracking (chain_demo.py:40-83): threshold sweep logic on CPU, oracle vs the reference's
+recorded chain, and the batched CUDA implementation vs the same recording (B200)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pips_oracle as po
+from pips_b200.chain import _threshold_table, pick_skip
+from tests.golden.make_golden import CHAIN_CASE, chain_inputs
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.npz"))
+
+
+def _gold_skips():
+    a = GOLD["chain/skips"]
+    n = CHAIN_CASE["N"]
+    lens, flat, out, k = a[:n], a[n:], [], 0
+    for L in lens:
+        out.append(list(flat[k:k + L]))
+        k += L
+    return out
+
+
+def _loop_skip(vis):                      # literal chain_demo.py:63-76
+    thr, si = 0.9, 7
+    while True:
+        if vis[si] > thr:
+            return si
+        si -= 1
+        if si == 1:
+            thr -= 0.02
+            si = 7
+
+
+def test_pick_skip_equals_reference_loop():
+    torch.manual_seed(0)
+    vis = torch.sigmoid(torch.randn(8, 500) * 2)
+    vis[:, 0] = 0.05                      # needs many sweeps
+    vis[:, 1] = torch.tensor([0.99, 0.99, 0.91, 0.2, 0.2, 0.2, 0.2, 0.95])
+    vis[:, 2] = 0.9                       # exactly at the first threshold: not '>' in fp32
+    got = pick_skip(vis, _threshold_table())
+    ref = torch.tensor([_loop_skip(vis[:, n]) for n in range(vis.shape[1])])
+    assert torch.equal(got.cpu(), ref)
+    assert int(got.min()) >= 2 and int(got.max()) <= 7
+
+
+def test_oracle_chain_matches_reference_recording():
+    c = CHAIN_CASE
+    sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+    rgbs, xy0 = chain_inputs(c)
+
+    def window(xys, seq, feat_init):
+        with torch.no_grad():
+            o = po.forward(sd, xys, seq, iters=c["iters"], stride=c["stride"], feat_init=feat_init, return_feat=True)
+        return o[0], o[2], o[3]
+
+    trajs, skips = po.chain_track(window, rgbs, xy0, iters=c["iters"])
+    assert skips == _gold_skips()
+    assert np.abs(trajs.numpy() - GOLD["chain/trajs"]).max() < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
+def test_batched_chain_matches_reference_recording(precision):
+    from pips_b200 import Pips
+    from pips_b200.chain import track_chain
+    c = CHAIN_CASE
+    sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+    model = Pips(S=8, stride=c["stride"], precision=precision).to("cuda:0").eval()
+    model.load_state_dict(sd, strict=True)
+    rgbs, xy0 = chain_inputs(c)
+    trajs, rounds = track_chain(model, rgbs.to("cuda:0"), xy0.to("cuda:0"), iters=c["iters"], return_rounds=True)
+    assert trajs.shape == (1, c["T"], c["N"], 2)
+    err = np.abs(trajs.cpu().numpy() - GOLD["chain/trajs"]).max()
+    print(f"chain {precision}: {rounds} batched rounds (reference: {sum(len(h) for h in _gold_skips())} model calls), max err {err:.2e} px")
+    assert rounds == max(len(h) for h in _gold_skips())
+    assert err < 2e-3

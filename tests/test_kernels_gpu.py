@@ -81,7 +81,7 @@ def test_init_gather_clamps_indices():
     ffeat = torch.empty(B * N, 128, device=DEV)
     ffeats = torch.empty(B * N, S, 128, device=DEV)
     cd = coords.to(DEV).contiguous()
-    L.check(lib.pips_init_gather(L.ptr(f32[0]), B, S, N, H, W, L.ptr(cd), L.ptr(ffeat), L.ptr(ffeats), _st()))
+    L.check(lib.pips_init_gather(L.ptr(f32[0]), B, S, N, H, W, L.ptr(cd), None, 0, L.ptr(ffeat), L.ptr(ffeats), _st()))
     _sync_check()
     assert (ffeat.cpu().reshape(B, N, 128) - ref).abs().max() < 1e-5
     assert torch.equal(ffeats.cpu(), ffeat.cpu().unsqueeze(1).expand(-1, S, -1))
@@ -128,7 +128,7 @@ def test_corr_gather(feat, B, N, H, W, wild):
     x_f = torch.full((M, 576), 7.0, device=DEV)
     cd, fd = coords.to(DEV).contiguous(), ff_rows.to(DEV).contiguous()
     td = po.times_axis(S).to(DEV)
-    L.check(lib.pips_corr_gather(L.ptr_array(lv), feat_dtype, B, S, N, H, W, L.ptr(cd), L.ptr(fd), L.ptr(td),
+    L.check(lib.pips_corr_gather(L.ptr_array(lv), feat_dtype, B, S, N, H, W, L.ptr(cd), L.ptr(fd), L.ptr(td), None, 0,
                                  L.ptr(x_hi), L.ptr(x_lo), L.ptr(x_f), 576, _st()))
     _sync_check()
     got = x_f.cpu().reshape(B * N, S, 576)

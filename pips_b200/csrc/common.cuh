@@ -57,6 +57,46 @@ __device__ __forceinline__ float gelu_fast(float x) {
     return x * (x > 0.0f ? 1.0f - q : q);
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot for two lanes of math) ----
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(reinterpret_cast<uint64_t&>(d))
+        : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)), "l"(reinterpret_cast<const uint64_t&>(c)));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 d;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<uint64_t&>(d)) : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+    return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 d;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<uint64_t&>(d)) : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+    return d;
+}
+__device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
+
+// gelu_fast on two values at once: identical arithmetic per lane (same roundings), half the issue slots.
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+    const float2 d = fma2(bcast2(0.27599915312530316f), make_float2(fabsf(x.x), fabsf(x.y)), bcast2(1.0f));
+    float2 t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(d.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(d.y));
+    float2 q = fma2(bcast2(-0.11345264142344407f), t, bcast2(0.44082137646110525f));
+    q = fma2(q, t, bcast2(-0.31387114090663395f));
+    q = fma2(q, t, bcast2(0.3221595132029044f));
+    q = fma2(q, t, bcast2(0.04671841449512236f));
+    q = fma2(q, t, bcast2(0.11762447426235381f));
+    const float2 ea = mul2(mul2(x, x), bcast2(-0.7213475204444817f));
+    float2 e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(ea.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(ea.y));
+    q = mul2(mul2(q, t), e);                           // Phi(-|x|)
+    const float2 omq = fma2(q, bcast2(-1.0f), bcast2(1.0f));
+    return mul2(x, make_float2(x.x > 0.0f ? omq.x : q.x, x.y > 0.0f ? omq.y : q.y));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

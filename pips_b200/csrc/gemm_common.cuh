@@ -56,7 +56,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& args, const uint3
     const bool row_ok = row < args.M;
     float f[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + b[j];
+    for (int j = 0; j < 32; j += 2) {
+        const float2 t = add2(make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), make_float2(b[j], b[j + 1]));
+        f[j] = t.x; f[j + 1] = t.y;
+    }
     if (next_col >= 0) load_bias_chunk(args, next_col, b);
     if (col >= args.N) return;                           // warp-uniform
     const bool full_chunk = col + 32 <= args.N;
@@ -73,10 +76,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& args, const uint3
                 uint32_t hw[4], lw[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float g0 = gelu_fast(f[8 * p + 2 * e]);
-                    const float g1 = gelu_fast(f[8 * p + 2 * e + 1]);
-                    hw[e] = cvt_bf16x2(g0, g1);
-                    lw[e] = cvt_bf16x2(g0 - __uint_as_float(hw[e] << 16), g1 - __uint_as_float(hw[e] & 0xffff0000u));
+                    const float2 g = gelu_fast2(make_float2(f[8 * p + 2 * e], f[8 * p + 2 * e + 1]));
+                    hw[e] = cvt_bf16x2(g.x, g.y);
+                    const float2 lo = fma2(make_float2(__uint_as_float(hw[e] << 16), __uint_as_float(hw[e] & 0xffff0000u)),
+                                           bcast2(-1.0f), g);                       // g - hi, one rounding
+                    lw[e] = cvt_bf16x2(lo.x, lo.y);
                 }
                 *reinterpret_cast<uint4*>(myrow + ((p ^ (lane & 7)) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                 *reinterpret_cast<uint4*>(myrow + (((p + 4) ^ (lane & 7)) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);

@@ -117,11 +117,12 @@ tokenmix_kernel(float* __restrict__ x, const float* __restrict__ ln1_w, const fl
                 const float* __restrict__ b2, const float* __restrict__ ln2_w, const float* __restrict__ ln2_b,
                 __nv_bfloat16* y_hi, __nv_bfloat16* y_lo, float* y_f32) {
     __shared__ float red[4][8];
-    __shared__ __align__(16) float s_w1[32 * 8], s_w2t[32 * 8];   // w1[j][s] and w2 transposed to [j][s]
+    // weights duplicated into (w, w) pairs so that one LDS.128 yields two packed FFMA2 operands
+    __shared__ __align__(16) float2 s_w1[32 * 8], s_w2t[32 * 8];  // w1[j][s] and w2 transposed to [j][s]
     __shared__ float s_b1[32], s_b2[8];
     for (int i = threadIdx.x; i < 256; i += TM_THREADS) {
-        s_w1[i] = w1[i];
-        s_w2t[(i & 31) * 8 + (i >> 5)] = w2[i];           // w2 is (8 s, 32 j)
+        s_w1[i] = bcast2(w1[i]);
+        s_w2t[(i & 31) * 8 + (i >> 5)] = bcast2(w2[i]);  // w2 is (8 s, 32 j)
     }
     if (threadIdx.x < 32) s_b1[threadIdx.x] = b1[threadIdx.x];
     if (threadIdx.x < 8) s_b2[threadIdx.x] = b2[threadIdx.x];
@@ -137,32 +138,42 @@ tokenmix_kernel(float* __restrict__ x, const float* __restrict__ ln1_w, const fl
     const float4 c1 = *reinterpret_cast<const float4*>(ln1_b + threadIdx.x * 4);
     layernorm8(xv, yv, g1, c1, red);          // also orders the smem weight writes before their use
 
-    // Conv1d(8->32,k=1) -> GELU -> Conv1d(32->8,k=1) across the frame axis, independently per channel
-    float z[8][4];
+    // Conv1d(8->32,k=1) -> GELU -> Conv1d(32->8,k=1) across the frame axis, independently per channel;
+    // channels are processed as two packed pairs (FFMA2).
+    float2 y2[8][2], z2[8][2];
 #pragma unroll
-    for (int s = 0; s < 8; ++s)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) z[s][c] = s_b2[s];
+    for (int s = 0; s < 8; ++s) {
+        y2[s][0] = make_float2(yv[s][0], yv[s][1]);
+        y2[s][1] = make_float2(yv[s][2], yv[s][3]);
+        z2[s][0] = z2[s][1] = bcast2(s_b2[s]);
+    }
 #pragma unroll 4
     for (int j = 0; j < 32; ++j) {
-        float h[4], wa[8], wb[8];
-        *reinterpret_cast<float4*>(wa) = *reinterpret_cast<const float4*>(s_w1 + j * 8);
-        *reinterpret_cast<float4*>(wa + 4) = *reinterpret_cast<const float4*>(s_w1 + j * 8 + 4);
-        *reinterpret_cast<float4*>(wb) = *reinterpret_cast<const float4*>(s_w2t + j * 8);
-        *reinterpret_cast<float4*>(wb + 4) = *reinterpret_cast<const float4*>(s_w2t + j * 8 + 4);
+        float2 wa[8], wb[8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) h[c] = s_b1[j];
+        for (int k = 0; k < 4; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(s_w1 + j * 8 + 2 * k);
+            const float4 b = *reinterpret_cast<const float4*>(s_w2t + j * 8 + 2 * k);
+            wa[2 * k] = make_float2(a.x, a.y); wa[2 * k + 1] = make_float2(a.z, a.w);
+            wb[2 * k] = make_float2(b.x, b.y); wb[2 * k + 1] = make_float2(b.z, b.w);
+        }
+        float2 h0 = bcast2(s_b1[j]), h1 = h0;
 #pragma unroll
-        for (int s = 0; s < 8; ++s)
+        for (int s = 0; s < 8; ++s) {
+            h0 = fma2(wa[s], y2[s][0], h0);
+            h1 = fma2(wa[s], y2[s][1], h1);
+        }
+        h0 = gelu_fast2(h0);
+        h1 = gelu_fast2(h1);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) h[c] = fmaf(wa[s], yv[s][c], h[c]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) h[c] = gelu_fast(h[c]);
-#pragma unroll
-        for (int s = 0; s < 8; ++s)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) z[s][c] = fmaf(wb[s], h[c], z[s][c]);
+        for (int s = 0; s < 8; ++s) {
+            z2[s][0] = fma2(wb[s], h0, z2[s][0]);
+            z2[s][1] = fma2(wb[s], h1, z2[s][1]);
+        }
     }
+    float z[8][4];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) { z[s][0] = z2[s][0].x; z[s][1] = z2[s][0].y; z[s][2] = z2[s][1].x; z[s][3] = z2[s][1].y; }
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
 #pragma unroll

@@ -117,6 +117,18 @@ int pips_inorm_apply(const float* y, const float* stats_y, const float* r, const
 int pips_resize_split3(const float* src, int N, int Hs, int Ws, int C, float* dst, int Ho, int Wo, int Ctot, int c_off,
                        void* stream);
 
+/* bf16 (hi, lo) flavours of the two functions above: the operand layout of pips_conv_tc (row stride pair_ld /
+ * Ctot channels; channels beyond C are left untouched and must be zero). */
+int pips_inorm_apply_pair(const float* y, const float* stats_y, const float* r, const float* stats_r, int relu_main, int relu_out,
+                          float* out_plain, void* out_hi, void* out_lo, int pair_ld, int N, int HW, int C, void* stream);
+int pips_resize_pair(const float* src, int N, int Hs, int Ws, int C, void* dst_hi, void* dst_lo, int Ho, int Wo, int Ctot, int c_off,
+                     void* stream);
+/* nn.Conv2d (3x3 / 1x1, stride 1 / 2; nets/pips.py:135-136,:170,:221-223) as an implicit GEMM on the tensor cores
+ * (tcgen05, CTA pairs, bf16x3).  x_hi/x_lo (N,H,W,Cp) bf16 with Cp % 64 == 0; w_hi/w_lo (BN, R*S*Cp) bf16,
+ * k = (r*S + s)*Cp + ci, BN = Cout rounded up to 64/128/256 with zero rows; out (N,Ho,Wo,Cout) fp32; bias may be NULL. */
+int pips_conv_tc(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp, const void* w_hi, const void* w_lo,
+                 int Cout, int R, int S, int stride, int pad, const float* bias, float* out, void* stream);
+
 /* Whole-iteration operator: everything between `for itr in range(iters)` and the append of
  * coords*stride (nets/pips.py:499-539, minus the dead fcp heat-map :504-511). */
 typedef struct pips_layer_weights {

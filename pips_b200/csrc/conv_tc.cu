@@ -1,0 +1,261 @@
+// 2-D convolution of the feature encoder as an implicit GEMM on CTA pairs (tcgen05.mma.cta_group::2).
+//
+//   out[n, oy, ox, co] = sum_{r,s,ci} in[n, oy*st + r - pad, ox*st + s - pad, ci] * w[co, r, s, ci]   (+ bias[co])
+//
+// for the 3x3 / 1x1, stride 1 / 2 convolutions of BasicEncoder's residual stages and head
+// (nets/pips.py:135-136, :170, :221-223).  Activations are channels-last bf16 (hi, lo) pairs (v ~= hi + lo)
+// written by pips_inorm_apply / pips_resize_pair, weights are packed (Cout_pad, taps*Cp) bf16 (hi, lo), and
+// every product is evaluated as hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM -- the same bf16x3
+// scheme as the mixer GEMMs (gemm_tc2.cu), whose pipeline this kernel reuses:
+//   GEMM-M  = output pixels, one CTA = TH rows x TW columns = 128 pixels (a pair = two adjacent tiles)
+//   GEMM-N  = output channels (64 / 128 / 256; W rows split between the two CTAs of the pair)
+//   GEMM-K  = taps x input channels; one K-chunk = 64 channels of one filter tap
+// The A tile of a K-chunk is ONE 4-D TMA box {64 ch, TW px, TH rows, 1 image} of the input at the tap's
+// offset (element strides = conv stride; out-of-bounds = zero padding), so no im2col buffer exists anywhere.
+#include "gemm_common.cuh"
+
+namespace pips {
+
+constexpr int C_THREADS = 384;
+constexpr uint32_t C_A_BYTES = 128 * BK * 2;          // 128 pixels x 64 channels bf16
+constexpr uint32_t C_STAGE_BYTES = 4 * C_A_BYTES;     // A_hi | W_hi(<=128 rows) | A_lo | W_lo
+constexpr int C_STAGES = 3;
+constexpr uint32_t C_SMEM_BYTES = C_STAGES * C_STAGE_BYTES + 1024 + 256;
+
+struct ConvArgs {
+    int N, Ho, Wo, Cout;        // output (NHWC fp32, row stride Cout)
+    int Cp;                     // padded input channels per tap (multiple of 64)
+    int R, S, stride, pad;      // filter taps, conv stride, zero padding
+    int TW, TH;                 // pixel tile: TW * TH == 128
+    int tiles_x, tiles_y;       // tiles per image
+    int BN;                     // GEMM-N tile == padded Cout: 64, 128 or 256
+    const float* bias;          // [Cout] or null
+    float* out;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const ConvArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_STAGES * C_STAGE_BYTES);
+    const uint32_t full0 = smem_u32(bars);
+    const uint32_t empty0 = full0 + 8 * C_STAGES;
+    const uint32_t tfull0 = empty0 + 8 * C_STAGES;
+    const uint32_t tempty0 = tfull0 + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C_STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+    const int tiles_img = a.tiles_x * a.tiles_y;
+    const int total_tiles = a.N * tiles_img;
+    const int pair_tiles = (total_tiles + 1) >> 1;
+    const int chunks = a.Cp / BK;
+    const int num_kb = a.R * a.S * chunks;
+    const uint32_t w_bytes = static_cast<uint32_t>(a.BN / 2) * BK * 2;       // this CTA's half of the weight tile
+    const uint32_t stage_tx = 2 * (C_A_BYTES + w_bytes);                      // per CTA: hi + lo
+
+    cluster_sync_all();
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
+        tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C_STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 2);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull0 + 8 * s, 1);
+            mbar_init(tempty0 + 8 * s, 2 * (C_THREADS - 128));
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_pair(smem_u32(tmem_slot), 512);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (warp == 0) {
+            // ------------------------------------------------------------ TMA producer (both CTAs)
+            if (lane == 0) {
+                uint32_t stage = 0, phase = 0;
+                for (int pt = pair; pt < pair_tiles; pt += num_pairs) {
+                    const int t = 2 * pt + static_cast<int>(rank);          // may be == total_tiles: all-zero tile
+                    const int img = t / tiles_img, rem = t - img * tiles_img;
+                    const int oy0 = (rem / a.tiles_x) * a.TH, ox0 = (rem % a.tiles_x) * a.TW;
+                    const int n0 = static_cast<int>(rank) * (a.BN / 2);
+                    int kb = 0;
+                    for (int r = 0; r < a.R; ++r) {
+                        for (int s = 0; s < a.S; ++s) {
+                            const int ix = ox0 * a.stride + s - a.pad, iy = oy0 * a.stride + r - a.pad;
+                            for (int c = 0; c < chunks; ++c, ++kb) {
+                                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                                const uint32_t fb = leader_addr(full0 + 8 * stage);
+                                if (leader) mbar_arrive_expect_tx(full0 + 8 * stage, 2 * stage_tx);
+                                else mbar_arrive_cluster(full0 + 8 * stage, 0);
+                                const uint32_t base = smem_u32(smem + stage * C_STAGE_BYTES);
+                                tma_load_4d_pair(base, &map_a_hi, fb, c * BK, ix, iy, img);
+                                tma_load_2d_pair(base + C_A_BYTES, &map_w_hi, fb, kb * BK, n0);
+                                tma_load_4d_pair(base + 2 * C_A_BYTES, &map_a_lo, fb, c * BK, ix, iy, img);
+                                tma_load_2d_pair(base + 3 * C_A_BYTES, &map_w_lo, fb, kb * BK, n0);
+                                if (++stage == C_STAGES) { stage = 0; phase ^= 1; }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            // ------------------------------------------------------------ MMA issuer (leader only)
+            if (leader && lane == 0) {
+                const uint32_t idesc = umma_idesc_bf16(256, a.BN);
+                uint32_t stage = 0, phase = 0;
+                int it = 0;
+                for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++it) {
+                    const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                    mbar_wait(tempty0 + 8 * as, aphase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + as * 256;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(full0 + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t base = smem_u32(smem + stage * C_STAGE_BYTES);
+                        const uint64_t a_hi = umma_desc_sw128(base);
+                        const uint64_t w_hi = umma_desc_sw128(base + C_A_BYTES);
+                        const uint64_t a_lo = umma_desc_sw128(base + 2 * C_A_BYTES);
+                        const uint64_t w_lo = umma_desc_sw128(base + 3 * C_A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t adv = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
+                            umma_f16_pair(d_tmem, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+                            umma_f16_pair(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
+                            umma_f16_pair(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                        }
+                        umma_commit_pair(empty0 + 8 * stage);
+                        if (kb == num_kb - 1) umma_commit_pair(tfull0 + 8 * as);
+                        if (++stage == C_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+        // ------------------------------------------------------------ epilogue (both CTAs, own 128 pixels)
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int half_cols = a.BN / 2;                       // 32, 64 or 128 columns per epilogue half
+        int it = 0;
+        for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++it) {
+            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+            const int t = 2 * pt + static_cast<int>(rank);
+            const int img = t / tiles_img, rem = t - img * tiles_img;
+            const int i = q * 32 + lane;                      // pixel index inside the tile
+            const int oy = (rem / a.tiles_x) * a.TH + i / a.TW, ox = (rem % a.tiles_x) * a.TW + i % a.TW;
+            const bool ok = t < total_tiles && oy < a.Ho && ox < a.Wo;
+            float* orow = a.out + ((static_cast<size_t>(img) * a.Ho + oy) * a.Wo + ox) * a.Cout;
+            mbar_wait(tfull0 + 8 * as, aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + as * 256 + half * half_cols + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < half_cols; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + c0, v);
+                tmem_ld_wait();
+                const int col = half * half_cols + c0;
+                if (ok && col < a.Cout) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (col + j < a.Cout) {               // Cout is a multiple of 4
+                            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                                   __uint_as_float(v[j + 3]));
+                            if (a.bias) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col + j));
+                                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                            }
+                            *reinterpret_cast<float4*>(orow + col + j) = o;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(tempty0 + 8 * as, 0);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+}
+
+}  // namespace pips
+
+using namespace pips;
+
+// x_hi/x_lo: (N, H, W, Cp) bf16; w_hi/w_lo: (BN, R*S*Cp) bf16 with BN = Cout rounded up to 64/128/256 (zero rows);
+// out: (N, Ho, Wo, Cout) fp32.
+extern "C" int pips_conv_tc(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp, const void* w_hi, const void* w_lo,
+                            int Cout, int R, int S, int stride, int pad, const float* bias, float* out, void* stream) {
+    if (!x_hi || !x_lo || !w_hi || !w_lo || !out) return fail("pips_conv_tc: null pointer");
+    if (N <= 0 || H <= 0 || W <= 0 || Cp <= 0 || (Cp % BK)) return fail("pips_conv_tc: Cp must be a positive multiple of 64");
+    if (Cout <= 0 || Cout > 256 || (Cout % 4)) return fail("pips_conv_tc: Cout must be a multiple of 4, at most 256");
+    if (R <= 0 || S <= 0 || R > 7 || S > 7 || (stride != 1 && stride != 2) || pad < 0) return fail("pips_conv_tc: unsupported filter geometry");
+    const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+    if (Ho <= 0 || Wo <= 0) return fail("pips_conv_tc: empty output");
+    ConvArgs a;
+    a.N = N; a.Ho = Ho; a.Wo = Wo; a.Cout = Cout; a.Cp = Cp; a.R = R; a.S = S; a.stride = stride; a.pad = pad;
+    a.BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+    // widest power-of-two tile row that does not exceed the output width (<= 128), the rest in rows
+    int tw = 128;
+    while (tw > 8 && tw > Wo) tw >>= 1;
+    if (stride == 2 && (tw - 1) * 2 + 1 > 256) tw = 64;
+    a.TW = tw; a.TH = 128 / tw;
+    a.tiles_x = (Wo + a.TW - 1) / a.TW; a.tiles_y = (Ho + a.TH - 1) / a.TH;
+    a.bias = bias; a.out = out;
+
+    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+    {
+        cuuint64_t gdim[4] = {static_cast<cuuint64_t>(Cp), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
+        cuuint64_t gstr[3] = {static_cast<cuuint64_t>(Cp) * 2, static_cast<cuuint64_t>(W) * Cp * 2, static_cast<cuuint64_t>(H) * W * Cp * 2};
+        cuuint32_t box[4] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>((a.TW - 1) * stride + 1),
+                             static_cast<cuuint32_t>((a.TH - 1) * stride + 1), 1};
+        cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+        if (!encode_tiled(&ma_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x_hi), gdim, gstr, box, estr, CU_TENSOR_MAP_SWIZZLE_128B) ||
+            !encode_tiled(&ma_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x_lo), gdim, gstr, box, estr, CU_TENSOR_MAP_SWIZZLE_128B))
+            return fail("pips_conv_tc: activation tensor map failed");
+    }
+    {
+        const int K = R * S * Cp;
+        cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(a.BN)};
+        cuuint64_t gstr[1] = {static_cast<cuuint64_t>(K) * 2};
+        cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(a.BN / 2)};
+        cuuint32_t estr[2] = {1, 1};
+        if (!encode_tiled(&mw_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_hi), gdim, gstr, box, estr, CU_TENSOR_MAP_SWIZZLE_128B) ||
+            !encode_tiled(&mw_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_lo), gdim, gstr, box, estr, CU_TENSOR_MAP_SWIZZLE_128B))
+            return fail("pips_conv_tc: weight tensor map failed");
+    }
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM_BYTES);
+        if (e != cudaSuccess) return fail_cuda("pips_conv_tc: smem attribute", e);
+        attr = true;
+    }
+    const int total_tiles = N * a.tiles_x * a.tiles_y;
+    const int pair_tiles = (total_tiles + 1) / 2;
+    const int max_pairs = sm_count() / 2;
+    const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
+    conv_tc_kernel<<<2 * pairs, C_THREADS, C_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(ma_hi, ma_lo, mw_hi, mw_lo, a);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail_cuda("pips_conv_tc: launch", e);
+}

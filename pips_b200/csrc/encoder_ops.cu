@@ -65,6 +65,7 @@ struct ApplyArgs {
     const float* r; const float* stats_r;               // optional residual (+ optional normalisation)
     int relu_main, relu_out;
     float* out_plain; float* out_split; int split_ld;   // split_ld = channels of the split tensor (>= 3*C)
+    __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int pair_ld;   // bf16 (hi, lo) operand of pips_conv_tc, row stride pair_ld >= C
     int HW, C;
 };
 
@@ -101,13 +102,20 @@ inorm_apply_kernel(const ApplyArgs a, size_t total4) {
             *reinterpret_cast<float4*>(d + a.C) = l;
             *reinterpret_cast<float4*>(d + 2 * a.C) = h;
         }
+        if (a.out_hi) {
+            __nv_bfloat16 h[4], l[4];
+            split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+            const size_t o = pix * a.pair_ld + c4 * 4;
+            *reinterpret_cast<uint2*>(a.out_hi + o) = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
+            *reinterpret_cast<uint2*>(a.out_lo + o) = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------- resize into the concat
 __global__ void __launch_bounds__(256)
-resize_split3_kernel(const float* __restrict__ src, int Hs, int Ws, int C, float* __restrict__ dst, int Ho, int Wo, int Ctot,
-                     int c_off, size_t total4) {
+resize_split3_kernel(const float* __restrict__ src, int Hs, int Ws, int C, float* __restrict__ dst, __nv_bfloat16* __restrict__ dst_hi,
+                     __nv_bfloat16* __restrict__ dst_lo, int Ho, int Wo, int Ctot, int c_off, size_t total4) {
     const int c4n = C >> 2;
     // at::native area_pixel_compute_scale(align_corners=true): (in - 1) / (out - 1), 0 when out == 1
     const float sh = Ho > 1 ? static_cast<float>(Hs - 1) / static_cast<float>(Ho - 1) : 0.f;
@@ -130,12 +138,20 @@ resize_split3_kernel(const float* __restrict__ src, int Hs, int Ws, int C, float
         v.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
         v.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z);
         v.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w);
-        const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-        const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-        float* d = dst + ((static_cast<size_t>(n) * Ho + oy) * Wo + ox) * (3 * static_cast<size_t>(Ctot)) + c_off + c4 * 4;
-        *reinterpret_cast<float4*>(d) = h;
-        *reinterpret_cast<float4*>(d + Ctot) = l;
-        *reinterpret_cast<float4*>(d + 2 * Ctot) = h;
+        if (dst) {
+            const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+            const float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+            float* d = dst + ((static_cast<size_t>(n) * Ho + oy) * Wo + ox) * (3 * static_cast<size_t>(Ctot)) + c_off + c4 * 4;
+            *reinterpret_cast<float4*>(d) = h;
+            *reinterpret_cast<float4*>(d + Ctot) = l;
+            *reinterpret_cast<float4*>(d + 2 * Ctot) = h;
+        } else {                                        // bf16 (hi, lo) pair, row stride Ctot
+            __nv_bfloat16 h[4], l[4];
+            split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+            const size_t o = ((static_cast<size_t>(n) * Ho + oy) * Wo + ox) * static_cast<size_t>(Ctot) + c_off + c4 * 4;
+            *reinterpret_cast<uint2*>(dst_hi + o) = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
+            *reinterpret_cast<uint2*>(dst_lo + o) = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
+        }
     }
 }
 
@@ -166,27 +182,55 @@ extern "C" int pips_inorm_stats(const float* y, int N, int HW, int C, float* par
     return e == cudaSuccess ? 0 : fail_cuda("pips_inorm_stats: finalize", e);
 }
 
-extern "C" int pips_inorm_apply(const float* y, const float* stats_y, const float* r, const float* stats_r, int relu_main,
-                                int relu_out, float* out_plain, float* out_split, int split_ld, int N, int HW, int C, void* stream) {
-    if (!y || (!out_plain && !out_split)) return fail("pips_inorm_apply: null pointer");
+static int inorm_apply_impl(const float* y, const float* stats_y, const float* r, const float* stats_r, int relu_main, int relu_out,
+                            float* out_plain, float* out_split, int split_ld, void* out_hi, void* out_lo, int pair_ld, int N, int HW,
+                            int C, void* stream) {
+    if (!y || (!out_plain && !out_split && !out_hi)) return fail("pips_inorm_apply: null pointer");
     if (N <= 0 || HW <= 0 || C <= 0 || (C % 4)) return fail("pips_inorm_apply: bad shape (C % 4 == 0)");
     if (out_split && (split_ld < 3 * C || (split_ld % 4))) return fail("pips_inorm_apply: split_ld must be >= 3*C and a multiple of 4");
+    if (out_hi && (!out_lo || pair_ld < C || (pair_ld % 4))) return fail("pips_inorm_apply: pair output needs out_lo and pair_ld >= C, % 4 == 0");
     ApplyArgs a;
     a.y = y; a.stats_y = stats_y; a.r = r; a.stats_r = stats_r; a.relu_main = relu_main; a.relu_out = relu_out;
     a.out_plain = out_plain; a.out_split = out_split; a.split_ld = split_ld; a.HW = HW; a.C = C;
+    a.out_hi = static_cast<__nv_bfloat16*>(out_hi); a.out_lo = static_cast<__nv_bfloat16*>(out_lo); a.pair_ld = pair_ld;
     const size_t total4 = static_cast<size_t>(N) * HW * (C / 4);
     inorm_apply_kernel<<<grid_for(total4), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, total4);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail_cuda("pips_inorm_apply", e);
 }
 
+extern "C" int pips_inorm_apply(const float* y, const float* stats_y, const float* r, const float* stats_r, int relu_main,
+                                int relu_out, float* out_plain, float* out_split, int split_ld, int N, int HW, int C, void* stream) {
+    return inorm_apply_impl(y, stats_y, r, stats_r, relu_main, relu_out, out_plain, out_split, split_ld, nullptr, nullptr, 0, N, HW, C,
+                            stream);
+}
+
+extern "C" int pips_inorm_apply_pair(const float* y, const float* stats_y, const float* r, const float* stats_r, int relu_main,
+                                     int relu_out, float* out_plain, void* out_hi, void* out_lo, int pair_ld, int N, int HW, int C,
+                                     void* stream) {
+    if (!out_hi) return fail("pips_inorm_apply_pair: null pointer");
+    return inorm_apply_impl(y, stats_y, r, stats_r, relu_main, relu_out, out_plain, nullptr, 0, out_hi, out_lo, pair_ld, N, HW, C, stream);
+}
+
+static int resize_impl(const float* src, int N, int Hs, int Ws, int C, float* dst, void* dst_hi, void* dst_lo, int Ho, int Wo, int Ctot,
+                       int c_off, void* stream) {
+    if (!src || (!dst && (!dst_hi || !dst_lo))) return fail("pips_resize: null pointer");
+    if (N <= 0 || Hs <= 0 || Ws <= 0 || Ho <= 0 || Wo <= 0 || (C % 4) || (Ctot % 4) || (c_off % 4) || c_off + C > Ctot)
+        return fail("pips_resize: bad shape");
+    const size_t total4 = static_cast<size_t>(N) * Ho * Wo * (C / 4);
+    resize_split3_kernel<<<grid_for(total4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, Hs, Ws, C, dst, static_cast<__nv_bfloat16*>(dst_hi), static_cast<__nv_bfloat16*>(dst_lo), Ho, Wo, Ctot, c_off, total4);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail_cuda("pips_resize", e);
+}
+
 extern "C" int pips_resize_split3(const float* src, int N, int Hs, int Ws, int C, float* dst, int Ho, int Wo, int Ctot, int c_off,
                                   void* stream) {
-    if (!src || !dst) return fail("pips_resize_split3: null pointer");
-    if (N <= 0 || Hs <= 0 || Ws <= 0 || Ho <= 0 || Wo <= 0 || (C % 4) || (Ctot % 4) || (c_off % 4) || c_off + C > Ctot)
-        return fail("pips_resize_split3: bad shape");
-    const size_t total4 = static_cast<size_t>(N) * Ho * Wo * (C / 4);
-    resize_split3_kernel<<<grid_for(total4), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, Hs, Ws, C, dst, Ho, Wo, Ctot, c_off, total4);
-    cudaError_t e = cudaGetLastError();
-    return e == cudaSuccess ? 0 : fail_cuda("pips_resize_split3", e);
+    if (!dst) return fail("pips_resize_split3: null pointer");
+    return resize_impl(src, N, Hs, Ws, C, dst, nullptr, nullptr, Ho, Wo, Ctot, c_off, stream);
+}
+
+extern "C" int pips_resize_pair(const float* src, int N, int Hs, int Ws, int C, void* dst_hi, void* dst_lo, int Ho, int Wo, int Ctot,
+                                int c_off, void* stream) {
+    return resize_impl(src, N, Hs, Ws, C, nullptr, dst_hi, dst_lo, Ho, Wo, Ctot, c_off, stream);
 }

@@ -36,9 +36,12 @@ def _w3(conv: torch.nn.Conv2d, pad_in_to: int = 0) -> torch.Tensor:
     return conv._w3cl
 
 
-def _conv(x3_nhwc: torch.Tensor, conv: torch.nn.Conv2d, pad_in_to: int = 0) -> torch.Tensor:
-    """x3_nhwc (N,H,W,3C) -> conv output as an (N,Ho,Wo,Cout) contiguous NHWC tensor."""
-    y = F.conv2d(x3_nhwc.permute(0, 3, 1, 2), _w3(conv, pad_in_to), conv.bias, conv.stride, conv.padding)
+def _conv(x3_nhwc: torch.Tensor, conv: torch.nn.Conv2d, pad_in_to: int = 0, bias: bool = False) -> torch.Tensor:
+    """x3_nhwc (N,H,W,3C) -> conv output as an (N,Ho,Wo,Cout) contiguous NHWC tensor.
+    ``bias=False`` for every convolution that feeds an InstanceNorm: a per-channel constant is removed again by
+    the normalisation (mean shifts by the same constant, variance unchanged), so adding it would only cost a
+    full element-wise pass; the result differs from the reference's by fp32 rounding only."""
+    y = F.conv2d(x3_nhwc.permute(0, 3, 1, 2), _w3(conv, pad_in_to), conv.bias if bias else None, conv.stride, conv.padding)
     y = y.permute(0, 2, 3, 1)
     return y if y.is_contiguous() else y.contiguous()
 
@@ -106,4 +109,105 @@ def fnet_fast(enc: Encoder, x: torch.Tensor) -> torch.Tensor:
 
     y = _conv(cat3, enc.conv2)
     _, A3 = ops.apply(y, ops.stats(y), relu_main=True)
-    return _conv(A3, enc.conv3)
+    return _conv(A3, enc.conv3, bias=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# 'tc' path: every 3x3 / 1x1 convolution on the tcgen05 implicit-GEMM kernel (csrc/conv_tc.cu), bf16x3 operands
+# --------------------------------------------------------------------------------------------------------------
+
+def _pad64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+def _packed_weight(conv: torch.nn.Conv2d):
+    """(Cout, Cin, R, S) fp32 -> ((BN, R*S*Cp) bf16 hi, lo) with k = (r*S + s)*Cp + ci; cached per weight version."""
+    w = conv.weight
+    key = (w.data_ptr(), w._version)
+    if getattr(conv, "_wtc_key", None) != key:
+        lib = L.load()
+        cout, cin, R, S = w.shape
+        cp = _pad64(cin)
+        bn = 64 if cout <= 64 else (128 if cout <= 128 else 256)
+        packed = torch.zeros(bn, R, S, cp, dtype=torch.float32, device=w.device)
+        packed[:cout, :, :, :cin] = w.detach().float().permute(0, 2, 3, 1)
+        packed = packed.reshape(bn, R * S * cp).contiguous()
+        hi = torch.empty_like(packed, dtype=torch.bfloat16)
+        lo = torch.empty_like(packed, dtype=torch.bfloat16)
+        L.check(lib.pips_split_bf16(L.ptr(packed), L.ptr(hi), L.ptr(lo), packed.numel(), _st()), "pips_split_bf16")
+        conv._wtc = (hi, lo)
+        conv._wtc_key = key
+    return conv._wtc
+
+
+class _Pair:
+    """bf16 (hi, lo) channels-last activation (N, H, W, Cp); channels beyond C stay zero."""
+
+    def __init__(self, N, H, W, C, device):
+        self.shape, self.C, self.Cp = (N, H, W), C, _pad64(C)
+        alloc = torch.zeros if self.Cp != C else torch.empty
+        self.hi = alloc(N, H, W, self.Cp, dtype=torch.bfloat16, device=device)
+        self.lo = alloc(N, H, W, self.Cp, dtype=torch.bfloat16, device=device)
+
+
+def conv_tc(x: _Pair, conv: torch.nn.Conv2d, bias: bool = False) -> torch.Tensor:
+    lib = L.load()
+    N, H, W = x.shape
+    cout, cin, R, S = conv.weight.shape
+    assert cin == x.C and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]
+    st, pad = conv.stride[0], conv.padding[0]
+    Ho, Wo = (H + 2 * pad - R) // st + 1, (W + 2 * pad - S) // st + 1
+    w_hi, w_lo = _packed_weight(conv)
+    out = torch.empty(N, Ho, Wo, cout, dtype=torch.float32, device=x.hi.device)
+    b = conv.bias.detach().float().contiguous() if bias and conv.bias is not None else None
+    L.check(lib.pips_conv_tc(L.ptr(x.hi), L.ptr(x.lo), N, H, W, x.Cp, L.ptr(w_hi), L.ptr(w_lo), cout, R, S, st, pad,
+                             L.ptr(b), L.ptr(out), _st()), "pips_conv_tc")
+    return out
+
+
+def _apply_pair(ops: _Ops, y, stats, r=None, stats_r=None, relu_main=True, relu_out=False, plain=False):
+    N, H, W, C = y.shape
+    out_p = torch.empty_like(y) if plain else None
+    pair = _Pair(N, H, W, C, y.device)
+    L.check(ops.lib.pips_inorm_apply_pair(L.ptr(y), L.ptr(stats), L.ptr(r), L.ptr(stats_r), int(relu_main), int(relu_out),
+                                          L.ptr(out_p), L.ptr(pair.hi), L.ptr(pair.lo), pair.Cp, N, H * W, C, _st()),
+            "pips_inorm_apply_pair")
+    return out_p, pair
+
+
+def fnet_tc(enc: Encoder, x: torch.Tensor) -> torch.Tensor:
+    """Same network as fnet_fast with the residual stages and the head on pips_conv_tc (tcgen05, bf16x3);
+    the 7x7 stem (3 input channels, K = 147) stays on the cuDNN 3xTF32 path."""
+    assert x.is_cuda and x.dtype == torch.float32
+    ops = _Ops(x.device)
+    N, _, H, W = x.shape
+    H8, W8 = H // enc.stride, W // enc.stride
+
+    xh = _tf32_hi(x)
+    z = torch.zeros(N, 1, H, W, dtype=torch.float32, device=x.device)
+    x12 = torch.cat([xh, z, x - xh, z, xh, z], dim=1).permute(0, 2, 3, 1).contiguous()
+    y = _conv(x12, enc.conv1, pad_in_to=4)
+    X, XP = _apply_pair(ops, y, ops.stats(y), relu_main=True, plain=True)
+
+    ctot = 64 + 96 + 128 + 128
+    cat = _Pair(N, H8, W8, ctot, x.device)
+    c_off = 0
+    for i in range(1, 5):
+        for blk in getattr(enc, f"layer{i}"):
+            y1 = conv_tc(XP, blk.conv1)
+            _, AP = _apply_pair(ops, y1, ops.stats(y1), relu_main=True)
+            y2 = conv_tc(AP, blk.conv2)
+            s2 = ops.stats(y2)
+            if blk.downsample is not None:
+                d = conv_tc(XP, blk.downsample[0])
+                X, XP = _apply_pair(ops, y2, s2, r=d, stats_r=ops.stats(d), relu_main=True, relu_out=True, plain=True)
+            else:
+                X, XP = _apply_pair(ops, y2, s2, r=X, relu_main=True, relu_out=True, plain=True)
+        Ns, Hs, Ws, Cs = X.shape
+        L.check(ops.lib.pips_resize_pair(L.ptr(X), Ns, Hs, Ws, Cs, L.ptr(cat.hi), L.ptr(cat.lo), H8, W8, cat.Cp, c_off, _st()),
+                "pips_resize_pair")
+        c_off += Cs
+
+    y = conv_tc(cat, enc.conv2)
+    _, AP = _apply_pair(ops, y, ops.stats(y), relu_main=True)
+    return conv_tc(AP, enc.conv3, bias=True)

@@ -11,9 +11,10 @@ Extra, optional knobs (keyword-only; the reference signature is unchanged):
   precision   'bf16x3' (default; tcgen05 with hi/lo-split bf16 operands, fp32-class accuracy, meets
               the 1e-3 px parity target), 'bf16' (fast, ~1e-2 px), 'fp32' (CUDA-core GEMMs, exact)
   feat_dtype  'fp32' (default) or 'bf16' storage of the correlation pyramid
-  fnet_mode   'fast' (default; channels-last, cuDNN TF32 tensor-core convolutions over hi/lo-split
-              operands = fp32-class accuracy, element-wise stages fused in libpips_b200), 'x3' (same
-              convolutions through eager torch ops) or 'plain' (strict fp32 cuDNN)
+  fnet_mode   'tc' (default; residual stages and head as tcgen05 implicit-GEMM convolutions with bf16x3
+              operands, element-wise stages fused, channels-last), 'fast' (cuDNN TF32 tensor-core
+              convolutions over hi/lo-split operands instead), 'x3' (the same cuDNN convolutions through
+              eager torch ops) or 'plain' (strict fp32 cuDNN)
 Environment overrides: PIPS_B200_PRECISION, PIPS_B200_FEAT, PIPS_B200_FNET.
 """
 from __future__ import annotations
@@ -109,10 +110,11 @@ class Pips(nn.Module):
         feat_dtype = feat_dtype or os.environ.get("PIPS_B200_FEAT", "fp32")
         self._engine = RefineEngine(precision=precision, feat_dtype=feat_dtype, max_seqs=max_seqs)
         self._shard = None                      # (rank, world, group) when particle-sharded
-        self.fnet_mode = fnet_mode or os.environ.get("PIPS_B200_FNET", "fast")
-        if self.fnet_mode not in ("fast", "x3", "plain"):
-            raise ValueError("fnet_mode must be 'fast' (channels-last, fused element-wise kernels, 3xTF32 convolutions), "
-                             "'x3' (3xTF32 convolutions through eager torch ops) or 'plain' (strict fp32 cuDNN)")
+        self.fnet_mode = fnet_mode or os.environ.get("PIPS_B200_FNET", "tc")
+        if self.fnet_mode not in ("tc", "fast", "x3", "plain"):
+            raise ValueError("fnet_mode must be 'tc' (tcgen05 implicit-GEMM convolutions, bf16x3), 'fast' (cuDNN 3xTF32 "
+                             "convolutions, channels-last, fused element-wise kernels), 'x3' (3xTF32 convolutions through "
+                             "eager torch ops) or 'plain' (strict fp32 cuDNN)")
 
     # ------------------------------------------------------------------ configuration
     @property
@@ -135,12 +137,12 @@ class Pips(nn.Module):
         # the split paths detach the weights: inference only (the training path keeps plain cuDNN + autograd)
         infer = x.is_cuda and not torch.is_grad_enabled()
         H8, W8 = H // self.stride, W // self.stride
-        if self.fnet_mode == "fast" and infer:
-            from .encoder_fast import fnet_fast
+        if self.fnet_mode in ("fast", "tc") and infer:
+            from .encoder_fast import fnet_fast, fnet_tc
             with _conv_math(allow_tf32=True):
-                f = fnet_fast(self.fnet, x.reshape(B * S, C, H, W))                 # (B*S, H8, W8, 128) NHWC
+                f = (fnet_tc if self.fnet_mode == "tc" else fnet_fast)(self.fnet, x.reshape(B * S, C, H, W))   # NHWC
             return f.reshape(B, S, H8, W8, self.latent_dim).permute(0, 1, 4, 2, 3)  # logical (B,S,128,H8,W8)
-        x3 = self.fnet_mode in ("x3", "fast") and infer
+        x3 = self.fnet_mode in ("x3", "fast", "tc") and infer
         self.fnet.mode = "x3" if x3 else "plain"
         with _conv_math(allow_tf32=x3):
             fmaps = self.fnet(x.reshape(B * S, C, H, W))

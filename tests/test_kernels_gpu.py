@@ -298,3 +298,33 @@ def test_update_and_vis_head():
     _sync_check()
     v_ref = torch.nn.functional.linear(ff_ref, sd["vis_predictor.0.weight"], sd["vis_predictor.0.bias"]).reshape(B, N, S).permute(0, 2, 1)
     assert (vis.cpu() - v_ref).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("N,H,W,cin,cout,k,stride,pad,bias", [
+    (2, 24, 40, 64, 64, 3, 1, 1, False),      # layer1-like, two tile rows
+    (1, 45, 80, 64, 64, 3, 1, 1, False),      # odd height, partial tiles
+    (2, 48, 64, 64, 96, 3, 2, 1, False),      # stride 2, Cout padded 96 -> 128
+    (2, 48, 64, 64, 96, 1, 2, 0, False),      # 1x1 stride-2 projection
+    (1, 23, 40, 96, 96, 3, 1, 1, False),      # Cin padded 96 -> 128
+    (1, 12, 16, 416, 256, 3, 1, 1, False),    # head conv, K = 9 x 448
+    (3, 12, 16, 256, 128, 1, 1, 0, True),     # final 1x1 with bias; odd number of tiles
+    (1, 192, 256, 64, 64, 3, 1, 1, False),    # full-size layer1 map: many tiles per pair
+])
+def test_conv_tc(N, H, W, cin, cout, k, stride, pad, bias):
+    from pips_b200.encoder_fast import _Pair, conv_tc
+    torch.manual_seed(17)
+    conv = torch.nn.Conv2d(cin, cout, k, stride=stride, padding=pad).to(DEV)
+    x = torch.randn(N, H, W, cin, device=DEV)
+    pair = _Pair(N, H, W, cin, DEV)
+    hi = x.to(torch.bfloat16)
+    pair.hi[..., :cin] = hi
+    pair.lo[..., :cin] = (x - hi.float()).to(torch.bfloat16)
+    out = conv_tc(pair, conv, bias=bias)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), conv.weight.double(),
+                                     conv.bias.double() if bias else None, stride=stride, padding=pad).permute(0, 2, 3, 1).float()
+    assert out.shape == ref.shape
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"conv_tc {cin}->{cout} k{k} s{stride}: max err {err:.2e} (|out| max {scale:.2f})")
+    assert err < 3e-4 * max(1.0, scale)

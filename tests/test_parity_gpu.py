@@ -91,14 +91,14 @@ def test_fnet_modes_agree(H, W, stride):
     sd = po.init_state_dict(seed=3)
     rgbs = po.smooth_video(1, 8, H, W, seed=77).to(DEV)
     outs = {}
-    for mode in ("plain", "x3", "fast"):
+    for mode in ("plain", "x3", "fast", "tc"):
         model = Pips(S=8, stride=stride, fnet_mode=mode).to(DEV).eval()
         model.load_state_dict(sd, strict=True)
         with torch.no_grad():
             outs[mode] = model.encode(rgbs).contiguous()
         assert outs[mode].shape == (1, 8, 128, H // stride, W // stride)
     scale = outs["plain"].abs().max().item()
-    for mode in ("x3", "fast"):
+    for mode in ("x3", "fast", "tc"):
         err = (outs[mode] - outs["plain"]).abs().max().item()
         print(f"fnet {mode} vs plain: max|err| {err:.3e} (|fmaps| max {scale:.2f})")
         assert err < 1e-3

@@ -275,6 +275,25 @@ def run_ours(args, rank, world, local_rank):
         roofline_corr["traffic"] = tr.get("corr_gather_bytes_per_launch")
     except Exception:
         pass
+    eager = None
+    if world == 1 and args.with_eager:
+        # the reference's algorithm as eager torch ops on THIS GPU (all-pairs volume, dense heat-map, strict-fp32
+        # cuDNN/cuBLAS) -- pips_b200/torch_path.py, which is pinned to the reference's outputs on CPU.  Context only.
+        from pips_b200.torch_path import forward_torch
+        mode = model.fnet_mode
+        model.fnet_mode = "plain"
+        with torch.no_grad():
+            for _ in range(2):
+                forward_torch(model, xys, rgbs.float(), iters=ITERS)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                forward_torch(model, xys, rgbs.float(), iters=ITERS)
+            e1.record(); torch.cuda.synchronize()
+        model.fnet_mode = mode
+        eager = {"value": updates / (e0.elapsed_time(e1) / 3e3), "unit": UNIT, "ms_per_step": e0.elapsed_time(e1) / 3,
+                 "what": "reference algorithm as eager torch ops on the same B200 (fp32, TF32 off)"}
     cpu = cpu_baseline_leg() if world == 1 and not args.no_cpu_baseline else None
     h2d = rgbs_h.numel() * rgbs_h.element_size() + xys_h.numel() * 4
     d2h = (B * S * n_global * 2 + B * S * n_global) * 4
@@ -294,6 +313,8 @@ def run_ours(args, rank, world, local_rank):
             "whole_path_tensor_frac": (updates * UNIT_FLOP / (t_dev / args.steps)) / 1e12 / pk["bf16_tflops_sustained"] / world}
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if eager is not None:
+        line["torch_eager_same_gpu"] = eager
     emit(line)
 
 
@@ -322,6 +343,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("PIPS_B200_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--feat", default=os.environ.get("PIPS_B200_FEAT", "fp32"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--with-eager", action="store_true", help="also time the eager-torch restatement of the reference on this GPU")
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default 1024 = BASELINE cfg2; 4096 = cfg3 on one GPU)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

@@ -256,7 +256,7 @@ def run_ours(args, rank, world, local_rank):
     achieved_tf = gemm_flop / (gemm_ms * 1e-3) / 1e12
     tc = args.precision != "fp32"
     mma_per_product = 3 if args.precision == "bf16x3" else 1
-    roofline = {"kernel": "gemm_tc_kernel (FC1+FC2 of the 12 channel-mixing blocks)" if tc else "gemm_f32_kernel",
+    roofline = {"kernel": "gemm_tc2_kernel (tcgen05 cta_group::2; FC1+FC2 of the 12 channel-mixing blocks)" if tc else "gemm_f32_kernel",
                 "bound": "tensor", "achieved": achieved_tf, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved_tf / pk["bf16_tflops_sustained"], "traffic": None,
                 "peak_source": pk["source"] + " (sustained bf16 cuBLAS)", "share_of_iteration": gemm_ms / sum(per_iter.values()),
@@ -303,7 +303,7 @@ def run_ours(args, rank, world, local_rank):
             "data": "synthetic",
             "config": {"workload": f"BASELINE cfg2 per GPU: B={B}, S={S}, {H}x{W} bf16 video, N={N_PER_GPU}/GPU (global N={n_global}), iters={ITERS}, stride={STRIDE}",
                        "precision": args.precision, "feat_dtype": args.feat, "parallelism": f"particle-sharded dp{world}" if world > 1 else "single GPU",
-                       "includes": "fnet + pyramid + 6 refinement iterations + vis head", "l2": "256 MB write between steps (L2 flushed); working set > L2"},
+                       "includes": "fnet (tcgen05 convs) + pyramid + 6 refinement iterations + vis head", "fnet_mode": model.fnet_mode, "l2": "256 MB write between steps (L2 flushed); working set > L2"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": updates / (t_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": t_e2e / args.steps * 1e3},

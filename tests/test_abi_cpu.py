@@ -49,3 +49,14 @@ def test_torch_modules_equal_oracle_on_cpu():
         rgb = po.smooth_video(1, 2, 64, 96)
         inp = (2 * (rgb / 255) - 1).reshape(2, 3, 64, 96)
         assert (m.fnet(inp) - po.fnet(sd, inp, 8)).abs().max() < 1e-6
+
+
+def test_edge_shapes_are_rejected_by_the_c_abi():
+    """Argument validation needs no GPU: empty problems, S != 8, bad leading dimensions."""
+    lib = L.load()
+    assert lib.pips_update(0, 0, 0, 0, 0, 0, 0, 0, 0, 8.0, 1, 8, 1, 0) != 0
+    assert b"null" in lib.pips_last_error()
+    assert lib.pips_conv_tc(1, 1, 1, 16, 16, 100, 1, 1, 64, 3, 3, 1, 1, 0, 1, 0) != 0        # Cp not a multiple of 64
+    assert lib.pips_conv_tc(1, 1, 1, 16, 16, 64, 1, 1, 64, 3, 3, 3, 1, 0, 1, 0) != 0         # stride 3
+    assert lib.pips_tokenmix(1, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0) != 0                  # zero sequences
+    assert lib.pips_pyramid_build(1, 8, 4, 4, None, None, 0) != 0                            # map too small for 4 levels

@@ -129,6 +129,13 @@ int pips_resize_pair(const float* src, int N, int Hs, int Ws, int C, void* dst_h
 int pips_conv_tc(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp, const void* w_hi, const void* w_lo,
                  int Cout, int R, int S, int stride, int pad, const float* bias, float* out, void* stream);
 
+int pips_conv_tc_aniso(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp, const void* w_hi, const void* w_lo,
+                       int Cout, int R, int S, int stride_y, int stride_x, int pad_y, int pad_x, const float* bias, float* out,
+                       void* stream);
+/* nets/pips.py:436 + the column unfolding of the 7x7/2 stem (:206): rgb (N,3,H,W) fp32 (dtype 0) or bf16 (dtype 1),
+ * 0..255 -> (N, H, Wo, 64) bf16 (hi, lo), channel k = s*3 + colour holds 2*(rgb/255)-1 at x = 2*ox + s - 3. */
+int pips_stem_pack(const void* rgb, int dtype, int N, int H, int W, void* out_hi, void* out_lo, void* stream);
+
 /* Whole-iteration operator: everything between `for itr in range(iters)` and the append of
  * coords*stride (nets/pips.py:499-539, minus the dead fcp heat-map :504-511). */
 typedef struct pips_layer_weights {

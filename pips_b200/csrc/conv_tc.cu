@@ -25,7 +25,7 @@ constexpr uint32_t C_SMEM_BYTES = C_STAGES * C_STAGE_BYTES + 1024 + 256;
 struct ConvArgs {
     int N, Ho, Wo, Cout;        // output (NHWC fp32, row stride Cout)
     int Cp;                     // padded input channels per tap (multiple of 64)
-    int R, S, stride, pad;      // filter taps, conv stride, zero padding
+    int R, S, sy, sx, py, px;   // filter taps, conv stride (rows, cols), zero padding (rows, cols)
     int TW, TH;                 // pixel tile: TW * TH == 128
     int tiles_x, tiles_y;       // tiles per image
     int BN;                     // GEMM-N tile == padded Cout: 64, 128 or 256
@@ -97,7 +97,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     int kb = 0;
                     for (int r = 0; r < a.R; ++r) {
                         for (int s = 0; s < a.S; ++s) {
-                            const int ix = ox0 * a.stride + s - a.pad, iy = oy0 * a.stride + r - a.pad;
+                            const int ix = ox0 * a.sx + s - a.px, iy = oy0 * a.sy + r - a.py;
                             for (int c = 0; c < chunks; ++c, ++kb) {
                                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
                                 const uint32_t fb = leader_addr(full0 + 8 * stage);
@@ -205,21 +205,22 @@ using namespace pips;
 
 // x_hi/x_lo: (N, H, W, Cp) bf16; w_hi/w_lo: (BN, R*S*Cp) bf16 with BN = Cout rounded up to 64/128/256 (zero rows);
 // out: (N, Ho, Wo, Cout) fp32.
-extern "C" int pips_conv_tc(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp, const void* w_hi, const void* w_lo,
-                            int Cout, int R, int S, int stride, int pad, const float* bias, float* out, void* stream) {
+static int conv_tc_impl(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp, const void* w_hi, const void* w_lo,
+                        int Cout, int R, int S, int sy, int sx, int py, int px, const float* bias, float* out, void* stream) {
     if (!x_hi || !x_lo || !w_hi || !w_lo || !out) return fail("pips_conv_tc: null pointer");
     if (N <= 0 || H <= 0 || W <= 0 || Cp <= 0 || (Cp % BK)) return fail("pips_conv_tc: Cp must be a positive multiple of 64");
     if (Cout <= 0 || Cout > 256 || (Cout % 4)) return fail("pips_conv_tc: Cout must be a multiple of 4, at most 256");
-    if (R <= 0 || S <= 0 || R > 7 || S > 7 || (stride != 1 && stride != 2) || pad < 0) return fail("pips_conv_tc: unsupported filter geometry");
-    const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+    if (R <= 0 || S <= 0 || R > 7 || S > 7 || (sy != 1 && sy != 2) || (sx != 1 && sx != 2) || py < 0 || px < 0)
+        return fail("pips_conv_tc: unsupported filter geometry");
+    const int Ho = (H + 2 * py - R) / sy + 1, Wo = (W + 2 * px - S) / sx + 1;
     if (Ho <= 0 || Wo <= 0) return fail("pips_conv_tc: empty output");
     ConvArgs a;
-    a.N = N; a.Ho = Ho; a.Wo = Wo; a.Cout = Cout; a.Cp = Cp; a.R = R; a.S = S; a.stride = stride; a.pad = pad;
+    a.N = N; a.Ho = Ho; a.Wo = Wo; a.Cout = Cout; a.Cp = Cp; a.R = R; a.S = S; a.sy = sy; a.sx = sx; a.py = py; a.px = px;
     a.BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
     // widest power-of-two tile row that does not exceed the output width (<= 128), the rest in rows
     int tw = 128;
     while (tw > 8 && tw > Wo) tw >>= 1;
-    if (stride == 2 && (tw - 1) * 2 + 1 > 256) tw = 64;
+    if (sx == 2 && (tw - 1) * 2 + 1 > 256) tw = 64;
     a.TW = tw; a.TH = 128 / tw;
     a.tiles_x = (Wo + a.TW - 1) / a.TW; a.tiles_y = (Ho + a.TH - 1) / a.TH;
     a.bias = bias; a.out = out;
@@ -228,9 +229,9 @@ extern "C" int pips_conv_tc(const void* x_hi, const void* x_lo, int N, int H, in
     {
         cuuint64_t gdim[4] = {static_cast<cuuint64_t>(Cp), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};
         cuuint64_t gstr[3] = {static_cast<cuuint64_t>(Cp) * 2, static_cast<cuuint64_t>(W) * Cp * 2, static_cast<cuuint64_t>(H) * W * Cp * 2};
-        cuuint32_t box[4] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>((a.TW - 1) * stride + 1),
-                             static_cast<cuuint32_t>((a.TH - 1) * stride + 1), 1};
-        cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride), static_cast<cuuint32_t>(stride), 1};
+        cuuint32_t box[4] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>((a.TW - 1) * sx + 1),
+                             static_cast<cuuint32_t>((a.TH - 1) * sy + 1), 1};
+        cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(sx), static_cast<cuuint32_t>(sy), 1};
         if (!encode_tiled(&ma_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x_hi), gdim, gstr, box, estr, CU_TENSOR_MAP_SWIZZLE_128B) ||
             !encode_tiled(&ma_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x_lo), gdim, gstr, box, estr, CU_TENSOR_MAP_SWIZZLE_128B))
             return fail("pips_conv_tc: activation tensor map failed");
@@ -258,4 +259,17 @@ extern "C" int pips_conv_tc(const void* x_hi, const void* x_lo, int N, int H, in
     conv_tc_kernel<<<2 * pairs, C_THREADS, C_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(ma_hi, ma_lo, mw_hi, mw_lo, a);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail_cuda("pips_conv_tc: launch", e);
+}
+
+extern "C" int pips_conv_tc(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp, const void* w_hi, const void* w_lo,
+                            int Cout, int R, int S, int stride, int pad, const float* bias, float* out, void* stream) {
+    return conv_tc_impl(x_hi, x_lo, N, H, W, Cp, w_hi, w_lo, Cout, R, S, stride, stride, pad, pad, bias, out, stream);
+}
+
+// Anisotropic form (separate row / column stride and padding): the 7x7 stem runs as a 7x1 convolution over the
+// column-unfolded image written by pips_stem_pack.
+extern "C" int pips_conv_tc_aniso(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp, const void* w_hi, const void* w_lo,
+                                  int Cout, int R, int S, int stride_y, int stride_x, int pad_y, int pad_x, const float* bias,
+                                  float* out, void* stream) {
+    return conv_tc_impl(x_hi, x_lo, N, H, W, Cp, w_hi, w_lo, Cout, R, S, stride_y, stride_x, pad_y, pad_x, bias, out, stream);
 }

@@ -155,6 +155,41 @@ resize_split3_kernel(const float* __restrict__ src, int Hs, int Ws, int C, float
     }
 }
 
+// ---------------------------------------------------------------------------------------- stem input
+// nets/pips.py:436 (2*(rgb/255)-1) fused with the column unfolding of the 7x7 / stride-2 stem (:206): for every
+// input row y and output column ox the 7 taps x 3 colours at x = 2*ox + s - 3 (zero outside the image) become 21
+// channels of a 64-channel bf16 (hi, lo) pixel; the stem is then a 7x1 convolution with row stride 2.
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem_pack_kernel(const T* __restrict__ rgb, int H, int W, int Wo, __nv_bfloat16* __restrict__ out_hi,
+                 __nv_bfloat16* __restrict__ out_lo, size_t total) {
+    // one thread per (n, y, ox, group of 4 channels); 16 groups per pixel, groups 6..15 are zero padding
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i & 15);
+        size_t p = i >> 4;
+        const int ox = static_cast<int>(p % Wo); p /= Wo;
+        const int y = static_cast<int>(p % H);
+        const size_t n = p / H;
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = g * 4 + e;                     // k = s*3 + colour
+            float v = 0.f;
+            if (k < 21) {
+                const int s = k / 3, c = k - 3 * s;
+                const int x = 2 * ox + s - 3;
+                if (x >= 0 && x < W) {
+                    const float raw = static_cast<float>(rgb[((n * 3 + c) * H + y) * static_cast<size_t>(W) + x]);
+                    v = 2.0f * (raw / 255.0f) - 1.0f;
+                }
+            }
+            split_bf16(v, h[e], l[e]);
+        }
+        *reinterpret_cast<uint2*>(out_hi + i * 4) = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
+        *reinterpret_cast<uint2*>(out_lo + i * 4) = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
+    }
+}
+
 }  // namespace pips
 
 using namespace pips;
@@ -233,4 +268,24 @@ extern "C" int pips_resize_split3(const float* src, int N, int Hs, int Ws, int C
 extern "C" int pips_resize_pair(const float* src, int N, int Hs, int Ws, int C, void* dst_hi, void* dst_lo, int Ho, int Wo, int Ctot,
                                 int c_off, void* stream) {
     return resize_impl(src, N, Hs, Ws, C, nullptr, dst_hi, dst_lo, Ho, Wo, Ctot, c_off, stream);
+}
+
+// rgb: (N, 3, H, W) fp32 (dtype 0) or bf16 (dtype 1), values 0..255; out_hi/out_lo: (N, H, Wo, 64) with Wo = (W - 1) / 2 + 1
+extern "C" int pips_stem_pack(const void* rgb, int dtype, int N, int H, int W, void* out_hi, void* out_lo, void* stream) {
+    if (!rgb || !out_hi || !out_lo) return fail("pips_stem_pack: null pointer");
+    if (N <= 0 || H <= 0 || W <= 0) return fail("pips_stem_pack: empty image");
+    const int Wo = (W - 1) / 2 + 1;
+    const size_t total = static_cast<size_t>(N) * H * Wo * 16;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == 0)
+        stem_pack_kernel<float><<<grid_for(total), 256, 0, st>>>(static_cast<const float*>(rgb), H, W, Wo, static_cast<__nv_bfloat16*>(out_hi),
+                                                                  static_cast<__nv_bfloat16*>(out_lo), total);
+    else if (dtype == 1)
+        stem_pack_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(rgb), H, W, Wo,
+                                                                          static_cast<__nv_bfloat16*>(out_hi),
+                                                                          static_cast<__nv_bfloat16*>(out_lo), total);
+    else
+        return fail("pips_stem_pack: dtype must be 0 (fp32) or 1 (bf16)");
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail_cuda("pips_stem_pack", e);
 }

@@ -175,18 +175,46 @@ def _apply_pair(ops: _Ops, y, stats, r=None, stats_r=None, relu_main=True, relu_
     return out_p, pair
 
 
-def fnet_tc(enc: Encoder, x: torch.Tensor) -> torch.Tensor:
-    """Same network as fnet_fast with the residual stages and the head on pips_conv_tc (tcgen05, bf16x3);
-    the 7x7 stem (3 input channels, K = 147) stays on the cuDNN 3xTF32 path."""
-    assert x.is_cuda and x.dtype == torch.float32
-    ops = _Ops(x.device)
-    N, _, H, W = x.shape
-    H8, W8 = H // enc.stride, W // enc.stride
+def _packed_stem_weight(conv: torch.nn.Conv2d):
+    """7x7x3 stem (Cout,3,7,7) -> (64, 7*64) bf16 (hi, lo): row tap r major, then k = s*3 + colour (21 of 64 used) --
+    the layout pips_stem_pack unfolds the image into."""
+    w = conv.weight
+    key = (w.data_ptr(), w._version)
+    if getattr(conv, "_wstem_key", None) != key:
+        lib = L.load()
+        cout = w.shape[0]
+        packed = torch.zeros(64, 7, 64, dtype=torch.float32, device=w.device)
+        packed[:cout, :, :21] = w.detach().float().permute(0, 2, 3, 1).reshape(cout, 7, 21)      # [co][r][s*3+ci]
+        packed = packed.reshape(64, 7 * 64).contiguous()
+        hi = torch.empty_like(packed, dtype=torch.bfloat16)
+        lo = torch.empty_like(packed, dtype=torch.bfloat16)
+        L.check(lib.pips_split_bf16(L.ptr(packed), L.ptr(hi), L.ptr(lo), packed.numel(), _st()), "pips_split_bf16")
+        conv._wstem = (hi, lo)
+        conv._wstem_key = key
+    return conv._wstem
 
-    xh = _tf32_hi(x)
-    z = torch.zeros(N, 1, H, W, dtype=torch.float32, device=x.device)
-    x12 = torch.cat([xh, z, x - xh, z, xh, z], dim=1).permute(0, 2, 3, 1).contiguous()
-    y = _conv(x12, enc.conv1, pad_in_to=4)
+
+def fnet_tc(enc: Encoder, rgb: torch.Tensor) -> torch.Tensor:
+    """rgb (N,3,H,W) fp32 or bf16 with values 0..255 (NOT normalised) -> feature maps (N,H/stride,W/stride,128) NHWC.
+    The whole encoder on libpips_b200: the 7x7/2 stem as a 7x1 tcgen05 convolution over the column-unfolded,
+    normalised image (pips_stem_pack), residual stages and head on pips_conv_tc, element-wise stages fused."""
+    assert rgb.is_cuda and rgb.dtype in (torch.float32, torch.bfloat16)
+    lib = L.load()
+    rgb = rgb.contiguous()
+    ops = _Ops(rgb.device)
+    N, _, H, W = rgb.shape
+    H8, W8 = H // enc.stride, W // enc.stride
+    x = rgb
+
+    Wo = (W - 1) // 2 + 1
+    unf = _Pair(N, H, Wo, 64, rgb.device)
+    L.check(lib.pips_stem_pack(L.ptr(rgb), 0 if rgb.dtype == torch.float32 else 1, N, H, W, L.ptr(unf.hi), L.ptr(unf.lo), _st()),
+            "pips_stem_pack")
+    w_hi, w_lo = _packed_stem_weight(enc.conv1)
+    Ho = (H - 1) // 2 + 1
+    y = torch.empty(N, Ho, Wo, 64, dtype=torch.float32, device=rgb.device)
+    L.check(lib.pips_conv_tc_aniso(L.ptr(unf.hi), L.ptr(unf.lo), N, H, Wo, 64, L.ptr(w_hi), L.ptr(w_lo), 64, 7, 1, 2, 1, 3, 0,
+                                   None, L.ptr(y), _st()), "pips_conv_tc_aniso")
     X, XP = _apply_pair(ops, y, ops.stats(y), relu_main=True, plain=True)
 
     ctot = 64 + 96 + 128 + 128

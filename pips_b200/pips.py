@@ -110,6 +110,7 @@ class Pips(nn.Module):
         feat_dtype = feat_dtype or os.environ.get("PIPS_B200_FEAT", "fp32")
         self._engine = RefineEngine(precision=precision, feat_dtype=feat_dtype, max_seqs=max_seqs)
         self._shard = None                      # (rank, world, group) when particle-sharded
+        self.shard_fnet = True                  # sharded runs also split the encoder's frames over the ranks
         self.fnet_mode = fnet_mode or os.environ.get("PIPS_B200_FNET", "tc")
         if self.fnet_mode not in ("tc", "fast", "x3", "plain"):
             raise ValueError("fnet_mode must be 'tc' (tcgen05 implicit-GEMM convolutions, bf16x3), 'fast' (cuDNN 3xTF32 "
@@ -133,14 +134,19 @@ class Pips(nn.Module):
     def encode(self, rgbs: torch.Tensor) -> torch.Tensor:
         """nets/pips.py:436-445: normalise to [-1,1], fnet per frame -> (B,S,128,H8,W8) fp32."""
         B, S, C, H, W = rgbs.shape
-        x = 2 * (rgbs.float() / 255.0) - 1.0
         # the split paths detach the weights: inference only (the training path keeps plain cuDNN + autograd)
-        infer = x.is_cuda and not torch.is_grad_enabled()
+        infer = rgbs.is_cuda and not torch.is_grad_enabled()
         H8, W8 = H // self.stride, W // self.stride
-        if self.fnet_mode in ("fast", "tc") and infer:
-            from .encoder_fast import fnet_fast, fnet_tc
+        if self.fnet_mode == "tc" and infer:
+            from .encoder_fast import fnet_tc
+            raw = rgbs if rgbs.dtype in (torch.float32, torch.bfloat16) else rgbs.float()
+            f = fnet_tc(self.fnet, raw.reshape(B * S, C, H, W))          # normalisation fused into the stem
+            return f.reshape(B, S, H8, W8, self.latent_dim).permute(0, 1, 4, 2, 3)   # logical (B,S,128,H8,W8)
+        x = 2 * (rgbs.float() / 255.0) - 1.0
+        if self.fnet_mode == "fast" and infer:
+            from .encoder_fast import fnet_fast
             with _conv_math(allow_tf32=True):
-                f = (fnet_tc if self.fnet_mode == "tc" else fnet_fast)(self.fnet, x.reshape(B * S, C, H, W))   # NHWC
+                f = fnet_fast(self.fnet, x.reshape(B * S, C, H, W))       # (B*S, H8, W8, 128) NHWC
             return f.reshape(B, S, H8, W8, self.latent_dim).permute(0, 1, 4, 2, 3)  # logical (B,S,128,H8,W8)
         x3 = self.fnet_mode in ("x3", "fast", "tc") and infer
         self.fnet.mode = "x3" if x3 else "plain"
@@ -164,7 +170,11 @@ class Pips(nn.Module):
             raise RuntimeError("pips_b200.Pips: the inference path is CUDA-only (sm_100a); move the model and "
                                "inputs to a CUDA device. There is no CPU fallback.")
         with torch.no_grad():
-            fmaps = self.encode(rgbs)
+            if self._shard is not None and self._shard[1] > 1 and self.shard_fnet and self.fnet_mode == "tc":
+                from .sharding import encode_sharded
+                fmaps = encode_sharded(self, rgbs)
+            else:
+                fmaps = self.encode(rgbs)
             return self.refine(xys, fmaps, coords_init=coords_init, feat_init=feat_init, iters=iters,
                                return_feat=return_feat)
 

@@ -73,3 +73,22 @@ def refine_sharded(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_init: 
     vis_full = vis_all.permute(1, 2, 0, 3).reshape(B, S, world * per)[:, :, :N].contiguous()
     ff_full = ff_all.permute(1, 0, 2, 3).reshape(B, world * per, -1)[:, :N].contiguous()
     return preds_full, vis_full, ff_full
+
+
+def encode_sharded(model, rgbs: torch.Tensor) -> torch.Tensor:
+    """Frame-sharded fnet: the B*S frames are independent (InstanceNorm is per frame,
+    nets/pips.py:412), so rank g encodes frames [g*F/G, (g+1)*F/G) and one all-gather of the channels-last feature
+    maps (<= a few tens of MB over NVLink) replaces G redundant encoder passes.  Bit-identical to the unsharded
+    encoder: every kernel of the 'tc' encoder works per image."""
+    rank, world, group = model._shard
+    B, S, C, H, W = rgbs.shape
+    F_ = B * S
+    per = (F_ + world - 1) // world
+    flat = rgbs.reshape(F_, C, H, W)
+    idx = torch.arange(rank * per, (rank + 1) * per, device=rgbs.device).clamp_(max=F_ - 1)     # tail ranks repeat the last frame
+    mine = model.encode(flat[idx].unsqueeze(0))                                                  # (1, per, 128, H8, W8), NHWC memory
+    H8, W8 = mine.shape[-2:]
+    local = mine[0].permute(0, 2, 3, 1).contiguous()                                             # (per, H8, W8, 128)
+    full = torch.empty(world * per, H8, W8, local.shape[-1], dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(full, local, group=group)
+    return full[:F_].reshape(B, S, H8, W8, -1).permute(0, 1, 4, 2, 3)                            # logical (B,S,128,H8,W8)

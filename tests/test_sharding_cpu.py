@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from pips_b200.sharding import refine_sharded, shard_bounds
+from pips_b200.sharding import encode_sharded, refine_sharded, shard_bounds
 
 
 def test_shard_bounds_cover_all_particles():
@@ -40,6 +40,11 @@ class _FakeModel:
         self._shard = shard
         self.engine = _FakeEngine()
 
+    def encode(self, rgbs):                      # per-frame function of the input, channels-last like the real encoder
+        B, S, C, H, W = rgbs.shape
+        f = rgbs.reshape(B * S, C, H, W).mean(1, keepdim=True).repeat(1, 128, 1, 1)[:, :, ::8, ::8]
+        return f.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2).reshape(B, S, 128, H // 8, W // 8)
+
 
 def _worker(rank, world, port, N, use_feat, q):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -53,6 +58,9 @@ def _worker(rank, world, port, N, use_feat, q):
         preds, vis, ff = refine_sharded(model, torch.zeros(B, S, 128, 4, 4), coords, feat, iters, 4.0)
         exp_p, exp_v, exp_f = _FakeEngine().refine(None, None, coords, feat, iters, 4.0)
         ok = torch.equal(preds, exp_p) and torch.equal(vis, exp_v) and torch.equal(ff, exp_f)
+        rgbs = torch.rand(B, 3, 3, 16, 24)       # 6 frames over 2 ranks; also an odd count: 3 frames
+        for clip in (rgbs, rgbs[:1]):
+            ok = ok and torch.equal(encode_sharded(model, clip), model.encode(clip))
         q.put((rank, bool(ok), tuple(preds.shape)))
     finally:
         dist.destroy_process_group()

@@ -229,7 +229,8 @@ def run_ours(args, rank, world, local_rank):
     t_dev = timed(step_device, args.steps)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    launches = model.engine.launches * args.steps
+    from pips_b200 import encoder_fast
+    launches = (model.engine.launches + (encoder_fast.LAUNCHES[0] if model.fnet_mode == 'tc' else 0)) * args.steps
     step_host()
     barrier()
     t_e2e = timed(step_host, args.steps)

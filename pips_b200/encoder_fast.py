@@ -18,6 +18,9 @@ from . import _lib as L
 from .encoder import Encoder, _tf32_hi
 
 
+LAUNCHES = [0]          # kernels of libpips_b200 launched by the last fnet_tc / fnet_fast call (bench accounting)
+
+
 def _st() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -58,6 +61,7 @@ class _Ops:
         partial = torch.empty(N, chunks, 2, C, dtype=torch.float32, device=self.dev)
         st = torch.empty(N, 2, C, dtype=torch.float32, device=self.dev)
         L.check(self.lib.pips_inorm_stats(L.ptr(y), N, hw, C, L.ptr(partial), chunks, L.ptr(st), _st()), "pips_inorm_stats")
+        LAUNCHES[0] += 2
         return st
 
     def apply(self, y, stats, r=None, stats_r=None, relu_main=True, relu_out=False, plain=False, split=True):
@@ -66,6 +70,7 @@ class _Ops:
         out_s = torch.empty(N, H, W, 3 * C, dtype=torch.float32, device=self.dev) if split else None
         L.check(self.lib.pips_inorm_apply(L.ptr(y), L.ptr(stats), L.ptr(r), L.ptr(stats_r), int(relu_main), int(relu_out),
                                           L.ptr(out_p), L.ptr(out_s), 3 * C, N, H * W, C, _st()), "pips_inorm_apply")
+        LAUNCHES[0] += 1
         return out_p, out_s
 
     def resize_into(self, src, dst3, c_off, ctot):
@@ -162,6 +167,7 @@ def conv_tc(x: _Pair, conv: torch.nn.Conv2d, bias: bool = False) -> torch.Tensor
     b = conv.bias.detach().float().contiguous() if bias and conv.bias is not None else None
     L.check(lib.pips_conv_tc(L.ptr(x.hi), L.ptr(x.lo), N, H, W, x.Cp, L.ptr(w_hi), L.ptr(w_lo), cout, R, S, st, pad,
                              L.ptr(b), L.ptr(out), _st()), "pips_conv_tc")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -172,6 +178,7 @@ def _apply_pair(ops: _Ops, y, stats, r=None, stats_r=None, relu_main=True, relu_
     L.check(ops.lib.pips_inorm_apply_pair(L.ptr(y), L.ptr(stats), L.ptr(r), L.ptr(stats_r), int(relu_main), int(relu_out),
                                           L.ptr(out_p), L.ptr(pair.hi), L.ptr(pair.lo), pair.Cp, N, H * W, C, _st()),
             "pips_inorm_apply_pair")
+    LAUNCHES[0] += 1
     return out_p, pair
 
 
@@ -200,6 +207,7 @@ def fnet_tc(enc: Encoder, rgb: torch.Tensor) -> torch.Tensor:
     normalised image (pips_stem_pack), residual stages and head on pips_conv_tc, element-wise stages fused."""
     assert rgb.is_cuda and rgb.dtype in (torch.float32, torch.bfloat16)
     lib = L.load()
+    LAUNCHES[0] = 0
     rgb = rgb.contiguous()
     ops = _Ops(rgb.device)
     N, _, H, W = rgb.shape
@@ -215,6 +223,7 @@ def fnet_tc(enc: Encoder, rgb: torch.Tensor) -> torch.Tensor:
     y = torch.empty(N, Ho, Wo, 64, dtype=torch.float32, device=rgb.device)
     L.check(lib.pips_conv_tc_aniso(L.ptr(unf.hi), L.ptr(unf.lo), N, H, Wo, 64, L.ptr(w_hi), L.ptr(w_lo), 64, 7, 1, 2, 1, 3, 0,
                                    None, L.ptr(y), _st()), "pips_conv_tc_aniso")
+    LAUNCHES[0] += 2                                   # stem_pack + stem conv
     X, XP = _apply_pair(ops, y, ops.stats(y), relu_main=True, plain=True)
 
     ctot = 64 + 96 + 128 + 128
@@ -234,6 +243,7 @@ def fnet_tc(enc: Encoder, rgb: torch.Tensor) -> torch.Tensor:
         Ns, Hs, Ws, Cs = X.shape
         L.check(ops.lib.pips_resize_pair(L.ptr(X), Ns, Hs, Ws, Cs, L.ptr(cat.hi), L.ptr(cat.lo), H8, W8, cat.Cp, c_off, _st()),
                 "pips_resize_pair")
+        LAUNCHES[0] += 1
         c_off += Cs
 
     y = conv_tc(cat, enc.conv2)

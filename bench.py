@@ -114,11 +114,18 @@ def host_threads() -> int:
 
 
 def make_inputs(n_global: int):
-    from oracle import pips_oracle as po          # input generator + weights only (not on the measured path)
-    rgbs = po.smooth_video(B, S, H, W, seed=1234).to(torch.bfloat16)       # integers 0..255: exact in bf16
-    xys = po.random_queries(B, n_global, H, W, seed=4321)
-    sd = po.init_state_dict(seed=0, head_scale=0.05)
-    return sd, rgbs, xys
+    """Synthetic clip + queries for the CUDA arm (product-side generators; the oracle is not involved)."""
+    from pips_b200 import synthetic
+    rgbs = synthetic.smooth_video(B, S, H, W, seed=1234).to(torch.bfloat16)       # integers 0..255: exact in bf16
+    xys = synthetic.random_queries(B, n_global, H, W, seed=4321)
+    return rgbs, xys
+
+
+def make_oracle_inputs():
+    """Same-shaped workload for the CPU legs, from the oracle's own generators and seeded weights."""
+    from oracle import pips_oracle as po
+    return (po.init_state_dict(seed=0, head_scale=0.05), po.smooth_video(B, S, H, W, seed=1234),
+            po.random_queries(B, N_PER_GPU, H, W, seed=4321))
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -131,7 +138,7 @@ def run_reference(args, rank, world):
     from oracle import pips_oracle as po
     cores = host_threads()
     torch.set_num_threads(cores)
-    sd, rgbs, xys = make_inputs(N_PER_GPU)
+    sd, rgbs, xys = make_oracle_inputs()
     bs, ns = 1, 256                                # reference-style chunk (test_on_davis.py:111-125 chunks N by 256)
     rg, xy = rgbs[:bs].float(), xys[:bs, :ns]
 
@@ -165,7 +172,7 @@ def cpu_baseline_leg():
     from oracle import pips_oracle as po
     cores = host_threads()
     torch.set_num_threads(cores)
-    sd, rgbs, xys = make_inputs(N_PER_GPU)
+    sd, rgbs, xys = make_oracle_inputs()
     bs, ns = 1, 256
     rg, xy = rgbs[:bs].float(), xys[:bs, :ns]
     with torch.no_grad():
@@ -182,14 +189,13 @@ def cpu_baseline_leg():
 
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
-    from pips_b200 import Pips
+    from pips_b200 import synthetic
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     n_global = N_PER_GPU * world
-    sd, rgbs_h, xys_h = make_inputs(n_global)
-    model = Pips(S=S, stride=STRIDE, precision=args.precision, feat_dtype=args.feat).to(dev).eval()
-    model.load_state_dict(sd, strict=True)
+    rgbs_h, xys_h = make_inputs(n_global)
+    model = synthetic.seeded_model(stride=STRIDE, seed=0, head_scale=0.05, precision=args.precision, feat_dtype=args.feat).to(dev).eval()
     if world > 1:
         model.shard_particles()
     rgbs_h, xys_h = rgbs_h.pin_memory(), xys_h.pin_memory()

@@ -2,17 +2,14 @@
 import os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import pips_oracle as po          # inputs / weights only
-from pips_b200 import Pips
+from pips_b200 import synthetic
 from pips_b200.chain import track_chain
 
 dev = torch.device("cuda", 0)
 T, H, W, N = 100, 360, 640, 512
-sd = po.init_state_dict(seed=0, head_scale=0.05)
-rgbs = po.smooth_video(1, T, H, W, seed=99).to(dev)
-xy0 = po.random_queries(1, N, H, W, seed=98).to(dev)
-model = Pips(S=8, stride=4).to(dev).eval()
-model.load_state_dict(sd)
+rgbs = synthetic.smooth_video(1, T, H, W, seed=99).to(dev)
+xy0 = synthetic.random_queries(1, N, H, W, seed=98).to(dev)
+model = synthetic.seeded_model(stride=4).to(dev).eval()
 for _ in range(2):
     trajs, rounds = track_chain(model, rgbs, xy0, iters=6, return_rounds=True)
 torch.cuda.synchronize()

@@ -6,24 +6,26 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import pips_oracle as po          # input generator / weights only
-from pips_b200 import Pips
-from tests.golden.make_golden import CASES, case_inputs
+from pips_b200 import synthetic
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 ok = True
-for name in ("rect_s4_oob", "warm_s8", "odd_s8"):
-    c = CASES[name]
-    sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
-    rgbs, xys, extra = case_inputs(c)
-    extra = {k: v.to(dev) for k, v in extra.items()}
-    single = Pips(S=8, stride=c["stride"]).to(dev).eval()
-    single.load_state_dict(sd)
-    sharded = Pips(S=8, stride=c["stride"]).to(dev).eval()
-    sharded.load_state_dict(sd)
+CASES = {"rect_s4": dict(B=2, H=128, W=192, N=20, stride=4, iters=6, warm=False),
+         "warm_s8": dict(B=1, H=128, W=160, N=10, stride=8, iters=2, warm=True),
+         "odd_s8": dict(B=1, H=184, W=360, N=17, stride=8, iters=4, warm=False)}
+for name, c in CASES.items():
+    rgbs = synthetic.smooth_video(c["B"], 8, c["H"], c["W"], seed=5)
+    xys = synthetic.random_queries(c["B"], c["N"], c["H"], c["W"], seed=6)
+    extra = {}
+    if c["warm"]:
+        g = torch.Generator().manual_seed(7)
+        extra = {"coords_init": (xys[:, None] + torch.cumsum(torch.randn(c["B"], 8, c["N"], 2, generator=g), 1)).to(dev),
+                 "feat_init": (torch.randn(c["B"], c["N"], 128, generator=g) * 0.5).to(dev)}
+    single = synthetic.seeded_model(stride=c["stride"], seed=3).to(dev).eval()
+    sharded = synthetic.seeded_model(stride=c["stride"], seed=3).to(dev).eval()
     sharded.shard_particles()
     with torch.no_grad():
         a = single(xys.to(dev), rgbs.to(dev), iters=c["iters"], return_feat=True, **extra)

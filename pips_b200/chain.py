@@ -63,27 +63,24 @@ def track_chain(model, rgbs: torch.Tensor, xy0: torch.Tensor, iters: int = 6, re
     feat: Optional[torch.Tensor] = None
     active = torch.arange(N, device=dev)
     rounds = 0
-    try:
-        while active.numel() > 0:
-            na = active.numel()
-            base = cur[active]
-            start = traj[base, active]                                                   # (na, 2) current position
-            coords = (start / stride).view(1, 1, na, 2).repeat(1, S_WIN, 1, 1)           # zero-velocity init, :453
-            fi = None if feat is None else feat[:, active]
-            preds, vis_e, ffeat = eng.refine(model, fmaps, coords, fi, iters, stride,
-                                             frame_base=base.view(1, na).to(torch.int32))
-            eng._pyramid_is_current = True                                               # same clip next round
-            if feat is None:
-                feat = ffeat                                                             # outs[3], carried (chain_demo.py:57)
-            xys = preds[-1][0]                                                           # (8, na, 2)
-            t_idx = base.view(1, na) + torch.arange(S_WIN, device=dev).view(S_WIN, 1)    # (8, na)
-            ok = t_idx < T                                                               # S_local truncation, :61
-            traj[t_idx[ok], active.view(1, na).expand(S_WIN, na)[ok]] = xys[ok]
-            si = pick_skip(torch.sigmoid(vis_e[0]), thr)
-            cur[active] = base + si
-            active = active[cur[active] < T]
-            rounds += 1
-    finally:
-        eng._pyramid_is_current = False
+    while active.numel() > 0:
+        na = active.numel()
+        base = cur[active]
+        start = traj[base, active]                                                   # (na, 2) current position
+        coords = (start / stride).view(1, 1, na, 2).repeat(1, S_WIN, 1, 1)           # zero-velocity init, :453
+        fi = None if feat is None else feat[:, active]
+        preds, vis_e, ffeat = eng.refine(model, fmaps, coords, fi, iters, stride,
+                                         frame_base=base.view(1, na).to(torch.int32),
+                                         reuse_pyramid=rounds > 0)                  # same clip every round
+        if feat is None:
+            feat = ffeat                                                             # outs[3], carried (chain_demo.py:57)
+        xys = preds[-1][0]                                                           # (8, na, 2)
+        t_idx = base.view(1, na) + torch.arange(S_WIN, device=dev).view(S_WIN, 1)    # (8, na)
+        ok = t_idx < T                                                               # S_local truncation, :61
+        traj[t_idx[ok], active.view(1, na).expand(S_WIN, na)[ok]] = xys[ok]
+        si = pick_skip(torch.sigmoid(vis_e[0]), thr)
+        cur[active] = base + si
+        active = active[cur[active] < T]
+        rounds += 1
     out = traj.unsqueeze(0)
     return (out, rounds) if return_rounds else out

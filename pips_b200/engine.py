@@ -165,7 +165,6 @@ class RefineEngine:
         self._pyr: Optional[Pyramid] = None
         self._times = None
         self._plans: Dict[tuple, "_GraphPlan"] = {}
-        self._pyramid_is_current = False        # set by callers that reuse one pyramid over many refine() calls
         self.use_graph = os.environ.get("PIPS_B200_GRAPH", "1") != "0"
         self.launches = 0                       # kernels launched by the last refine() call
 
@@ -238,14 +237,15 @@ class RefineEngine:
         return launches + 1
 
     def refine(self, module, fmaps: torch.Tensor, coords: torch.Tensor, feat_init: Optional[torch.Tensor],
-               iters: int, stride: float, on_iter=None, frame_base: Optional[torch.Tensor] = None
-               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+               iters: int, stride: float, on_iter=None, frame_base: Optional[torch.Tensor] = None,
+               reuse_pyramid: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """fmaps (B,S,128,H8,W8) fp32, coords (B,S,N,2) fp32 in feature-map pixels.
         Returns preds (iters,B,S,N,2) in input pixels, vis_e (B,S,N) logits, ffeat (B,N,128).
         ``on_iter(it, coords_px)`` (optional) is called once per iteration when the particles fit one
         chunk -- the sharded path hangs its per-iteration all-gather there.
         ``frame_base`` (B,N) int32 (optional): chained tracking -- fmaps then holds T >= 1 frames per batch
-        element and track (b,n) works on frames min(frame_base[b,n] + s, T-1), s = 0..7."""
+        element and track (b,n) works on frames min(frame_base[b,n] + s, T-1), s = 0..7.
+        ``reuse_pyramid``: the pyramid built by the previous call is still valid (same fmaps; chained rounds)."""
         lib = L.load()
         B, T, Cc, H8, W8 = fmaps.shape
         S = coords.shape[1]
@@ -291,7 +291,7 @@ class RefineEngine:
             fb = None if frame_base is None else (frame_base if whole else frame_base[:, n0:n1].contiguous())
             self.launches += self._enqueue(lib, w.c, pyr, ws, fmaps2d, c, c0, ffeat, ffeats, fi, out, v, B, S, nc, H8, W8,
                                            iters, stride, on_iter if whole else None,
-                                           build_pyramid=(n0 == 0 and not self._pyramid_is_current), frame_base=fb, T=T)
+                                           build_pyramid=(n0 == 0 and not reuse_pyramid), frame_base=fb, T=T)
             if not whole:
                 preds[:, :, :, n0:n1] = out
                 vis[:, :, n0:n1] = v

@@ -89,6 +89,12 @@ int pips_tokenmix(float* x, int seqs, const float* ln1_w, const float* ln1_b,
                   const float* w1 /* (32,8) */, const float* b1, const float* w2 /* (8,32) */, const float* b2,
                   const float* ln2_w, const float* ln2_b, void* y_hi, void* y_lo, float* y_f32, void* stream);
 
+/* the same with the two contractions as tcgen05 MMAs (channels as the M dimension, bf16x3 folded into K); bf16
+ * outputs only.  Selected inside pips_tokenmix by PIPS_B200_TOKENMIX=tc; see csrc/tokenmix_tc.cu for its status. */
+int pips_tokenmix_tc(float* x, int seqs, const float* ln1_w, const float* ln1_b, const float* w1, const float* b1,
+                     const float* w2, const float* b2, const float* ln2_w, const float* ln2_b, void* y_hi, void* y_lo,
+                     void* stream);
+
 /* nets/pips.py:120-121: final LayerNorm(512) then mean over the S rows of each sequence. */
 int pips_ln_pool(const float* x, int seqs, const float* ln_w, const float* ln_b,
                  void* p_hi, void* p_lo, float* p_f32, void* stream);

@@ -31,6 +31,13 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
     lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
+// two floats -> packed bf16x2 (round to nearest even), `lo_elem` in the low half
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+
 __device__ __forceinline__ float gelu_exact(float v) {
     // nn.GELU() default (approximate='none'): 0.5 x (1 + erf(x / sqrt(2)))
     return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));

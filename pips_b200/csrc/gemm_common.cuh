@@ -38,13 +38,6 @@ __device__ __forceinline__ void load_bias_chunk(const GemmArgs& args, int col, f
     }
 }
 
-// two floats -> packed bf16x2 (round to nearest even), `lo_elem` in the low half
-__device__ __forceinline__ uint32_t cvt_bf16x2(float lo_elem, float hi_elem) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
-    return r;
-}
-
 // Epilogue of one 32-column chunk of the warp's 32 output rows (one row per thread): bias, then GELU + (hi, lo)
 // split, or fp32 store with optional residual.  `col` and the chunk predicates are warp-uniform.
 // `b` holds this chunk's bias on entry; once it is consumed the bias of column `next_col` (if >= 0) is loaded into

@@ -142,3 +142,24 @@ def test_cpu_inputs_fail_loudly():
     model = Pips(S=8, stride=8).eval()
     with pytest.raises(RuntimeError, match="CUDA-only"):
         model(torch.zeros(1, 4, 2), torch.zeros(1, 8, 3, 64, 64), iters=1)
+
+
+def test_demo_configuration_matches_oracle():
+    """BASELINE configs[0]: 8 x 360x640, N = 256 (16x16 grid as demo.py:32-36), iters = 6, B = 1, stride 4 --
+    the reference's own CPU-runnable case; the oracle runs live on the host (local-correlation formulation)."""
+    H, W, N_ = 360, 640, 16
+    sd = po.init_state_dict(seed=21, head_scale=0.05)
+    rgbs = po.smooth_video(1, 8, H, W, seed=22)
+    gy, gx = torch.meshgrid(torch.arange(N_).float(), torch.arange(N_).float(), indexing="ij")
+    xy = torch.stack([8 + gx.reshape(1, -1) / float(N_ - 1) * (W - 16), 8 + gy.reshape(1, -1) / float(N_ - 1) * (H - 16)], dim=-1)
+    with torch.no_grad():
+        ref = po.forward(sd, xy, rgbs, iters=6, stride=4)
+    model = Pips(S=8, stride=4).to(DEV).eval()
+    model.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        preds, preds2, vis_e, _ = model(xy.to(DEV), rgbs.to(DEV), iters=6)
+    err = (preds[-1].cpu() - ref[0][-1]).abs().max().item()
+    print(f"demo configuration (360x640, N=256, stride 4, iters 6): max err {err:.2e} px")
+    assert err < 1e-3
+    assert (vis_e.cpu() - ref[2]).abs().max() < 5e-3
+    assert len(preds2) == 10

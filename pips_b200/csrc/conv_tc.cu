@@ -18,9 +18,9 @@ namespace pips {
 
 constexpr int C_THREADS = 384;
 constexpr uint32_t C_A_BYTES = 128 * BK * 2;          // 128 pixels x 64 channels bf16
-constexpr uint32_t C_STAGE_BYTES = 4 * C_A_BYTES;     // A_hi | W_hi(<=128 rows) | A_lo | W_lo
-constexpr int C_STAGES = 3;
-constexpr uint32_t C_SMEM_BYTES = C_STAGES * C_STAGE_BYTES + 1024 + 256;
+constexpr int C_MAX_STAGES = 8;
+constexpr uint32_t C_RING_BYTES = 192 * 1024;         // smem ring: stage = A_hi | A_lo | W_hi | W_lo, 2*(16 KB + BN/2*128 B)
+constexpr uint32_t C_SMEM_BYTES = C_RING_BYTES + 1024 + 256;
 
 struct ConvArgs {
     int N, Ho, Wo, Cout;        // output (NHWC fp32, row stride Cout)
@@ -29,6 +29,7 @@ struct ConvArgs {
     int TW, TH;                 // pixel tile: TW * TH == 128
     int tiles_x, tiles_y;       // tiles per image
     int BN;                     // GEMM-N tile == padded Cout: 64, 128 or 256
+    int stages;                 // ring depth: 3 (BN = 256) .. 4 (BN = 64)
     const float* bias;          // [Cout] or null
     float* out;
 };
@@ -38,12 +39,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const ConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_STAGES * C_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_RING_BYTES);
     const uint32_t full0 = smem_u32(bars);
-    const uint32_t empty0 = full0 + 8 * C_STAGES;
-    const uint32_t tfull0 = empty0 + 8 * C_STAGES;
+    const uint32_t empty0 = full0 + 8 * C_MAX_STAGES;
+    const uint32_t tfull0 = empty0 + 8 * C_MAX_STAGES;
     const uint32_t tempty0 = tfull0 + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C_STAGES + 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C_MAX_STAGES + 4);
+    const int C_STAGES = a.stages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -57,6 +59,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int num_kb = a.R * a.S * chunks;
     const uint32_t w_bytes = static_cast<uint32_t>(a.BN / 2) * BK * 2;       // this CTA's half of the weight tile
     const uint32_t stage_tx = 2 * (C_A_BYTES + w_bytes);                      // per CTA: hi + lo
+    const uint32_t C_STAGE_BYTES = stage_tx;                                  // multiple of 1 KB for every BN
+    const uint32_t off_w_hi = 2 * C_A_BYTES, off_w_lo = 2 * C_A_BYTES + w_bytes;
 
     cluster_sync_all();
     if (warp == 0 && lane == 0) {
@@ -105,9 +109,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                                 else mbar_arrive_cluster(full0 + 8 * stage, 0);
                                 const uint32_t base = smem_u32(smem + stage * C_STAGE_BYTES);
                                 tma_load_4d_pair(base, &map_a_hi, fb, c * BK, ix, iy, img);
-                                tma_load_2d_pair(base + C_A_BYTES, &map_w_hi, fb, kb * BK, n0);
-                                tma_load_4d_pair(base + 2 * C_A_BYTES, &map_a_lo, fb, c * BK, ix, iy, img);
-                                tma_load_2d_pair(base + 3 * C_A_BYTES, &map_w_lo, fb, kb * BK, n0);
+                                tma_load_4d_pair(base + C_A_BYTES, &map_a_lo, fb, c * BK, ix, iy, img);
+                                tma_load_2d_pair(base + off_w_hi, &map_w_hi, fb, kb * BK, n0);
+                                tma_load_2d_pair(base + off_w_lo, &map_w_lo, fb, kb * BK, n0);
                                 if (++stage == C_STAGES) { stage = 0; phase ^= 1; }
                             }
                         }
@@ -131,9 +135,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         tc_fence_after();
                         const uint32_t base = smem_u32(smem + stage * C_STAGE_BYTES);
                         const uint64_t a_hi = umma_desc_sw128(base);
-                        const uint64_t w_hi = umma_desc_sw128(base + C_A_BYTES);
-                        const uint64_t a_lo = umma_desc_sw128(base + 2 * C_A_BYTES);
-                        const uint64_t w_lo = umma_desc_sw128(base + 3 * C_A_BYTES);
+                        const uint64_t a_lo = umma_desc_sw128(base + C_A_BYTES);
+                        const uint64_t w_hi = umma_desc_sw128(base + off_w_hi);
+                        const uint64_t w_lo = umma_desc_sw128(base + off_w_lo);
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             const uint64_t adv = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
@@ -217,6 +221,11 @@ static int conv_tc_impl(const void* x_hi, const void* x_lo, int N, int H, int W,
     ConvArgs a;
     a.N = N; a.Ho = Ho; a.Wo = Wo; a.Cout = Cout; a.Cp = Cp; a.R = R; a.S = S; a.sy = sy; a.sx = sx; a.py = py; a.px = px;
     a.BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+    {
+        const uint32_t stage = 2 * (C_A_BYTES + static_cast<uint32_t>(a.BN / 2) * BK * 2);
+        int st = static_cast<int>(C_RING_BYTES / stage);
+        a.stages = st > C_MAX_STAGES ? C_MAX_STAGES : st;      // BN 256: 3 x 64 KB, 128: 4 x 48 KB, 64: 4 x 40 KB
+    }
     // widest power-of-two tile row that does not exceed the output width (<= 128), the rest in rows
     int tw = 128;
     while (tw > 8 && tw > Wo) tw >>= 1;

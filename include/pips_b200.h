@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PIPS_B200_ABI_VERSION 1
+#define PIPS_B200_ABI_VERSION 2
 
 enum { PIPS_S = 8, PIPS_C = 128, PIPS_LEVELS = 4, PIPS_RADIUS = 3 };
 enum { PIPS_KITCHEN = 519, PIPS_KITCHEN_PAD = 576, PIPS_DIM = 512, PIPS_HIDDEN = 2048, PIPS_DEPTH = 12, PIPS_HEAD = 1040 };
@@ -99,14 +99,54 @@ int pips_tokenmix_tc(float* x, int seqs, const float* ln1_w, const float* ln1_b,
 int pips_ln_pool(const float* x, int seqs, const float* ln_w, const float* ln_b,
                  void* p_hi, void* p_lo, float* p_f32, void* stream);
 
+/* ---- results written straight into every rank's memory over NVLink ("fusing the coord
+ * all-gather into the update epilogue") ----
+ * Particle-sharded runs: rank g owns particles [n_offset, n_offset + N) of n_total.  out[r] is rank r's copy of the
+ * FULL (B,S,n_total,2) result of the current iteration, mapped into this process (pips_peer_open; out[own rank] is
+ * the local allocation).  The update kernel stores its slice into all of them, so after pips_peer_barrier every
+ * rank holds the whole result and no collective library call sits on the data path.  n_peers == 0: off. */
+#define PIPS_MAX_PEERS 16
+typedef struct pips_peer_out {
+    float* out[PIPS_MAX_PEERS];
+    int n_peers, n_offset, n_total;
+} pips_peer_out;
+
+/* cudaMalloc + cudaIpcGetMemHandle: *ptr is the local allocation, handle (64 bytes) goes to the other ranks. */
+int pips_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+/* cudaIpcOpenMemHandle (peer access enabled lazily) / cudaIpcCloseMemHandle / cudaFree */
+int pips_peer_open(const unsigned char* handle64, void** ptr);
+int pips_peer_close(void* ptr);
+int pips_peer_free(void* ptr);
+/* copy src (rows, cols) fp32, contiguous, into dst[r] (rows, cols_total) at column col_offset, for r < n_peers */
+int pips_peer_scatter(const float* src, int rows, int cols, float* const* dst, int n_peers, int cols_total, int col_offset,
+                      void* stream);
+/* flag barrier across the ranks of one node: store `epoch` into flags[r][rank] of every rank r (system-scope release
+ * after a system fence), then wait until flags[rank][r] >= epoch for all r.  flags[r] is rank r's int[PIPS_MAX_PEERS]
+ * array as mapped here.  Traps after timeout_ms (a lost rank must not hang the device). */
+int pips_peer_barrier(int* const* flags, int rank, int n_peers, int epoch, int timeout_ms, void* stream);
+
 /* nets/pips.py:525-539: split delta, ffeats += GELU(Linear(GroupNorm(1,128)(dfeat))), coords += dcoord,
  * re-lock frame 0, emit coords*stride.  delta is (B*N, S*130). */
 int pips_update(const float* delta, float* coords, const float* coords0, float* ffeats,
                 const float* gn_w, const float* gn_b, const float* wu /* (128,128) */, const float* bu,
                 float* out_px /* (B,S,N,2) */, float stride, int B, int S, int N, void* stream);
+/* pips_update that also stores coords*stride into every rank's full-size result (peer may be NULL) */
+int pips_update_peer(const float* delta, float* coords, const float* coords0, float* ffeats,
+                     const float* gn_w, const float* gn_b, const float* wu, const float* bu,
+                     float* out_px, float stride, int B, int S, int N, const pips_peer_out* peer, void* stream);
 
 /* nets/pips.py:559: vis_e = Linear(128,1)(ffeats) -> (B,S,N) logits */
 int pips_vis_head(const float* ffeats, const float* w, const float* b, float* vis, int B, int S, int N, void* stream);
+
+/* nets/pips.py:504-511 for chosen particles only: the dense score map
+ *   fcp[b,s,j,:,:] = sum_l interpolate(<ffeats[b,s,sel[j]], fmaps_l[b,s]> / sqrt(C), (H8,W8), bilinear, align_corners=True)
+ * read from the pyramid levels (channels-last, feat_dtype); ffeats is the loop state ((b*N+n), s, c).
+ * sel[n_sel]: particle indices in [0,N); slot[n_sel] (or NULL = identity): position of query j in the output;
+ * out element (b*S+s, slot, y, x) lives at out[(b*S+s)*out_frame_stride + (slot*H8 + y)*W8 + x].
+ * scratch: pips_heatmap_scratch_floats(B*S, n_sel, H8, W8) floats. */
+size_t pips_heatmap_scratch_floats(int frames, int n_sel, int H8, int W8);
+int pips_heatmap(const void* const* lvl, int feat_dtype, int B, int S, int N, int H8, int W8, const float* ffeats,
+                 const int* sel, const int* slot, int n_sel, float* scratch, float* out, size_t out_frame_stride, void* stream);
 
 /* v -> (hi, lo) bf16 with hi = rn(v), lo = rn(v - hi); lo may be NULL.  Used to pack weights. */
 int pips_split_bf16(const float* src, void* hi, void* lo, size_t n, void* stream);
@@ -185,6 +225,7 @@ typedef struct pips_problem {
     float stride;
     const int* frame_base;                /* NULL, or [B*N] window starts for chained tracking         */
     int frames_per_batch;                 /* frames per batch element in the pyramid when frame_base   */
+    pips_peer_out peer;                   /* n_peers > 0: also scatter coords*stride to every rank     */
 } pips_problem;
 
 /* DeltaBlock.forward on prepared input rows (nets/pips.py:304-311, mixer :111-123): x0 -> ws->delta */

@@ -10,6 +10,7 @@ import os
 
 from . import _build
 
+ABI_VERSION = 2            # PIPS_B200_ABI_VERSION of include/pips_b200.h
 DEPTH = 12
 LEVELS = 4
 KPAD = 576
@@ -49,10 +50,17 @@ class Workspace(C.Structure):
                                      "h_hi", "h_lo", "h_f32", "p_hi", "p_lo", "p_f32", "delta")])
 
 
+MAX_PEERS = 16
+
+
+class PeerOut(C.Structure):
+    _fields_ = [("out", _p * MAX_PEERS), ("n_peers", _i), ("n_offset", _i), ("n_total", _i)]
+
+
 class Problem(C.Structure):
     _fields_ = [("B", _i), ("S", _i), ("N", _i), ("H", _i), ("W", _i), ("feat_dtype", _i), ("precision", _i),
                 ("lvl", _p * LEVELS), ("times", _p), ("coords", _p), ("coords0", _p), ("ffeats", _p), ("stride", _f),
-                ("frame_base", _p), ("frames_per_batch", _i)]
+                ("frame_base", _p), ("frames_per_batch", _i), ("peer", PeerOut)]
 
 
 _SIGNATURES = {
@@ -62,6 +70,15 @@ _SIGNATURES = {
     "pips_pyramid_build_nhwc": (_i, [_p, _i, _i, _i, C.POINTER(_p), C.POINTER(_p), _p]),
     "pips_init_gather": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p]),
     "pips_corr_gather": (_i, [C.POINTER(_p), _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p, _i, _p]),
+    "pips_peer_alloc": (_i, [C.c_size_t, C.POINTER(_p), C.c_char_p]),
+    "pips_peer_open": (_i, [C.c_char_p, C.POINTER(_p)]),
+    "pips_peer_close": (_i, [_p]),
+    "pips_peer_free": (_i, [_p]),
+    "pips_peer_scatter": (_i, [_p, _i, _i, C.POINTER(_p), _i, _i, _i, _p]),
+    "pips_peer_barrier": (_i, [C.POINTER(_p), _i, _i, _i, _i, _p]),
+    "pips_update_peer": (_i, [_p] * 9 + [_f, _i, _i, _i, C.POINTER(PeerOut), _p]),
+    "pips_heatmap_scratch_floats": (C.c_size_t, [_i, _i, _i, _i]),
+    "pips_heatmap": (_i, [C.POINTER(_p), _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _p, C.c_size_t, _p]),
     "pips_gemm_tc": (_i, [_p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _i, _p, _p, _i, _p]),
     "pips_gemm_f32": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _i, _p, _i, _p]),
     "pips_tokenmix": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
@@ -106,7 +123,7 @@ def load(build_if_missing: bool = True):
         fn = getattr(lib, name)          # AttributeError here == missing export: fail loudly
         fn.restype = res
         fn.argtypes = args
-    if lib.pips_abi_version() != 1:
+    if lib.pips_abi_version() != ABI_VERSION:
         raise RuntimeError("libpips_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -144,6 +144,6 @@ extern "C" int pips_refine_iter(const pips_problem* p, const pips_weights* w, co
     if (rc) return rc;
     rc = pips_mixer_forward(w, ws, seqs, p->precision, stream);
     if (rc) return rc;
-    return pips_update(ws->delta, p->coords, p->coords0, p->ffeats, w->gn_w, w->gn_b, w->upd_w, w->upd_b, out_px, p->stride,
-                       p->B, p->S, p->N, stream);
+    return pips_update_peer(ws->delta, p->coords, p->coords0, p->ffeats, w->gn_w, w->gn_b, w->upd_w, w->upd_b, out_px,
+                            p->stride, p->B, p->S, p->N, &p->peer, stream);
 }

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256)
 update_kernel(const float* __restrict__ delta, float* __restrict__ coords, const float* __restrict__ coords0,
               float* __restrict__ ffeats, const float* __restrict__ gn_w, const float* __restrict__ gn_b,
               const float* __restrict__ wu, const float* __restrict__ bu, float* __restrict__ out_px, float stride,
-              int B, int S, int N) {
+              int B, int S, int N, const pips_peer_out peer) {
     extern __shared__ float sm[];
     float* s_wt = sm;                         // [128 k][129]  wt[k][j] = wu[j][k]
     float* s_g = sm + 128 * 129;              // [64 rows][132]
@@ -221,6 +221,13 @@ update_kernel(const float* __restrict__ delta, float* __restrict__ coords, const
             else { cx = coords[ci] + d[0]; cy = coords[ci + 1] + d[1]; }    // :533
             coords[ci] = cx; coords[ci + 1] = cy;
             out_px[ci] = cx * stride; out_px[ci + 1] = cy * stride;         // :538
+            if (peer.n_peers > 0) {
+                // the all-gather of the prediction, fused: this rank's slice goes straight into every rank's
+                // full (B,S,n_total,2) result over NVLink (peer-mapped stores; visibility: pips_peer_barrier)
+                const size_t gi = ((static_cast<size_t>(b) * S + s) * peer.n_total + peer.n_offset + n) * 2;
+                const float2 v = make_float2(cx * stride, cy * stride);
+                for (int p = 0; p < peer.n_peers; ++p) *reinterpret_cast<float2*>(peer.out[p] + gi) = v;
+            }
         }
     }
     __syncthreads();
@@ -327,6 +334,23 @@ extern "C" int pips_ln_pool(const float* x, int seqs, const float* ln_w, const f
 extern "C" int pips_update(const float* delta, float* coords, const float* coords0, float* ffeats, const float* gn_w,
                            const float* gn_b, const float* wu, const float* bu, float* out_px, float stride, int B, int S,
                            int N, void* stream) {
+    return pips_update_peer(delta, coords, coords0, ffeats, gn_w, gn_b, wu, bu, out_px, stride, B, S, N, nullptr, stream);
+}
+
+extern "C" int pips_update_peer(const float* delta, float* coords, const float* coords0, float* ffeats, const float* gn_w,
+                                const float* gn_b, const float* wu, const float* bu, float* out_px, float stride, int B,
+                                int S, int N, const pips_peer_out* peer, void* stream) {
+    pips_peer_out po;
+    po.n_peers = 0;
+    po.n_offset = 0;
+    po.n_total = N;
+    if (peer && peer->n_peers > 0) {
+        po = *peer;
+        if (po.n_peers > PIPS_MAX_PEERS) return fail("pips_update: more than PIPS_MAX_PEERS ranks");
+        if (po.n_offset < 0 || po.n_offset + N > po.n_total) return fail("pips_update: particle slice outside n_total");
+        for (int r = 0; r < po.n_peers; ++r)
+            if (!po.out[r] || (reinterpret_cast<uintptr_t>(po.out[r]) & 7)) return fail("pips_update: null or misaligned peer result");
+    }
     if (!delta || !coords || !coords0 || !ffeats || !gn_w || !gn_b || !wu || !bu || !out_px) return fail("pips_update: null pointer");
     if (S != PIPS_S) return fail("pips_update: S must be 8");
     if (B <= 0 || N <= 0) return fail("pips_update: empty problem");
@@ -339,7 +363,7 @@ extern "C" int pips_update(const float* delta, float* coords, const float* coord
         attr = true;
     }
     update_kernel<<<(rows + UP_ROWS - 1) / UP_ROWS, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-        delta, coords, coords0, ffeats, gn_w, gn_b, wu, bu, out_px, stride, B, S, N);
+        delta, coords, coords0, ffeats, gn_w, gn_b, wu, bu, out_px, stride, B, S, N, po);
     LAUNCH_CHECK("pips_update");
     return 0;
 }

@@ -201,6 +201,33 @@ def _packed_stem_weight(conv: torch.nn.Conv2d):
     return conv._wstem
 
 
+# ---- weight-pack hooks (pips_b200/pack.py): enumerate, export and adopt the packed filters ------------------
+
+def packed_convs(enc: Encoder):
+    """(dotted name, module) of every convolution the 'tc' path packs, in module order."""
+    return [(n, m) for n, m in enc.named_modules() if isinstance(m, torch.nn.Conv2d)]
+
+
+def packed_filter(enc: Encoder, name: str, conv: torch.nn.Conv2d):
+    return _packed_stem_weight(conv) if conv is enc.conv1 else _packed_weight(conv)
+
+
+def adopt_filter(enc: Encoder, name: str, conv: torch.nn.Conv2d, hi: torch.Tensor, lo: torch.Tensor) -> None:
+    """Install an already packed (hi, lo) filter as the cache entry of ``conv``'s current weight version."""
+    w = conv.weight
+    key = (w.data_ptr(), w._version)
+    if conv is enc.conv1:
+        expect = (64, 7 * 64)
+        conv._wstem, conv._wstem_key = (hi, lo), key
+    else:
+        cout, cin, R, S = w.shape
+        bn = 64 if cout <= 64 else (128 if cout <= 128 else 256)
+        expect = (bn, R * S * _pad64(cin))
+        conv._wtc, conv._wtc_key = (hi, lo), key
+    if tuple(hi.shape) != expect or tuple(lo.shape) != expect or hi.dtype != torch.bfloat16 or hi.device != w.device:
+        raise L.PipsCudaError(f"pips_b200: packed filter {name} has shape {tuple(hi.shape)}, expected {expect}")
+
+
 def fnet_tc(enc: Encoder, rgb: torch.Tensor) -> torch.Tensor:
     """rgb (N,3,H,W) fp32 or bf16 with values 0..255 (NOT normalised) -> feature maps (N,H/stride,W/stride,128) NHWC.
     The whole encoder on libpips_b200: the 7x7/2 stem as a 7x1 tcgen05 convolution over the column-unfolded,

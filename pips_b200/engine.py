@@ -28,61 +28,100 @@ class PackedWeights:
     Dense-layer weights are kept as nn.Linear stores them ((out, in) == N x K, K-major), split into a
     bf16 (hi, lo) pair for the tcgen05 path; the first Linear's K is zero-padded 519 -> 576 and the
     last Linear's N 1040 -> 1280 so that TMA boxes never leave the allocation.
+
+    ``self.t`` holds every tensor under a stable name ("layer3.fc1_w_hi", "head_b", ...); the names are
+    the fields of ``pips_weights`` / ``pips_layer_weights`` in include/pips_b200.h, which is also the
+    manifest of the on-disk pack (pips_b200/pack.py).
     """
 
-    def __init__(self, module, stream):
+    def __init__(self, module=None, stream=None, tensors: Optional[Dict[str, torch.Tensor]] = None):
+        self.c = L.Weights()
+        if tensors is not None:
+            self.t = dict(tensors)
+            self.device = self.t["gn_w"].device
+        else:
+            self.t = self._pack(module, stream)
+            self.device = self.t["gn_w"].device
+        if self.device.type != "cuda":
+            raise L.PipsCudaError("pips_b200: the refinement path needs the module on a CUDA device")
+        self._bind()
+
+    @staticmethod
+    def _pack(module, stream) -> Dict[str, torch.Tensor]:
         lib = L.load()
         sd = {k: v.detach() for k, v in module.state_dict().items()}
         dev = sd["norm.weight"].device
         if dev.type != "cuda":
             raise L.PipsCudaError("pips_b200: the refinement path needs the module on a CUDA device")
-        self.device = dev
-        self.keep = []                       # tensors referenced by raw pointer from the struct
-        self.c = L.Weights()
+        t: Dict[str, torch.Tensor] = {}
 
-        def f32(t):
-            t = t.to(torch.float32).contiguous()
-            self.keep.append(t)
-            return t
+        def f32(name, v):
+            t[name] = v.to(torch.float32).contiguous().clone()
 
-        def split(t):
-            t = f32(t)
-            hi = torch.empty(t.shape, dtype=torch.bfloat16, device=dev)
-            lo = torch.empty(t.shape, dtype=torch.bfloat16, device=dev)
-            L.check(lib.pips_split_bf16(L.ptr(t), L.ptr(hi), L.ptr(lo), t.numel(), stream), "pips_split_bf16")
-            self.keep += [hi, lo]
-            return hi, lo, t
+        def split(name, v):
+            f32(name + "_f32", v)
+            src = t[name + "_f32"]
+            hi = torch.empty(src.shape, dtype=torch.bfloat16, device=dev)
+            lo = torch.empty(src.shape, dtype=torch.bfloat16, device=dev)
+            L.check(lib.pips_split_bf16(L.ptr(src), L.ptr(hi), L.ptr(lo), src.numel(), stream), "pips_split_bf16")
+            t[name + "_hi"], t[name + "_lo"] = hi, lo
 
         td = "delta_block.to_delta"
         w0 = torch.zeros(L.DIM, L.KPAD, dtype=torch.float32, device=dev)
         w0[:, :519] = sd[f"{td}.0.weight"]
-        hi, lo, f = split(w0)
-        self.c.in_w_hi, self.c.in_w_lo, self.c.in_w_f32 = L.ptr(hi), L.ptr(lo), L.ptr(f)
-        self.c.in_b = L.ptr(f32(sd[f"{td}.0.bias"]))
+        split("in_w", w0)
+        f32("in_b", sd[f"{td}.0.bias"])
         for l in range(L.DEPTH):
-            p = f"{td}.{l + 1}"
-            lw = self.c.layer[l]
-            lw.ln1_w, lw.ln1_b = L.ptr(f32(sd[p + ".0.norm.weight"])), L.ptr(f32(sd[p + ".0.norm.bias"]))
-            lw.tok_w1 = L.ptr(f32(sd[p + ".0.fn.0.weight"].reshape(4 * S_FRAMES, S_FRAMES)))
-            lw.tok_b1 = L.ptr(f32(sd[p + ".0.fn.0.bias"]))
-            lw.tok_w2 = L.ptr(f32(sd[p + ".0.fn.3.weight"].reshape(S_FRAMES, 4 * S_FRAMES)))
-            lw.tok_b2 = L.ptr(f32(sd[p + ".0.fn.3.bias"]))
-            lw.ln2_w, lw.ln2_b = L.ptr(f32(sd[p + ".1.norm.weight"])), L.ptr(f32(sd[p + ".1.norm.bias"]))
-            hi, lo, f = split(sd[p + ".1.fn.0.weight"])
-            lw.fc1_w_hi, lw.fc1_w_lo, lw.fc1_w_f32 = L.ptr(hi), L.ptr(lo), L.ptr(f)
-            lw.fc1_b = L.ptr(f32(sd[p + ".1.fn.0.bias"]))
-            hi, lo, f = split(sd[p + ".1.fn.3.weight"])
-            lw.fc2_w_hi, lw.fc2_w_lo, lw.fc2_w_f32 = L.ptr(hi), L.ptr(lo), L.ptr(f)
-            lw.fc2_b = L.ptr(f32(sd[p + ".1.fn.3.bias"]))
-        self.c.out_ln_w, self.c.out_ln_b = L.ptr(f32(sd[f"{td}.13.weight"])), L.ptr(f32(sd[f"{td}.13.bias"]))
+            p, q = f"{td}.{l + 1}", f"layer{l}."
+            f32(q + "ln1_w", sd[p + ".0.norm.weight"])
+            f32(q + "ln1_b", sd[p + ".0.norm.bias"])
+            f32(q + "tok_w1", sd[p + ".0.fn.0.weight"].reshape(4 * S_FRAMES, S_FRAMES))
+            f32(q + "tok_b1", sd[p + ".0.fn.0.bias"])
+            f32(q + "tok_w2", sd[p + ".0.fn.3.weight"].reshape(S_FRAMES, 4 * S_FRAMES))
+            f32(q + "tok_b2", sd[p + ".0.fn.3.bias"])
+            f32(q + "ln2_w", sd[p + ".1.norm.weight"])
+            f32(q + "ln2_b", sd[p + ".1.norm.bias"])
+            split(q + "fc1_w", sd[p + ".1.fn.0.weight"])
+            f32(q + "fc1_b", sd[p + ".1.fn.0.bias"])
+            split(q + "fc2_w", sd[p + ".1.fn.3.weight"])
+            f32(q + "fc2_b", sd[p + ".1.fn.3.bias"])
+        f32("out_ln_w", sd[f"{td}.13.weight"])
+        f32("out_ln_b", sd[f"{td}.13.bias"])
         wh = torch.zeros(L.HEAD_PAD, L.DIM, dtype=torch.float32, device=dev)
         wh[:L.HEAD] = sd[f"{td}.15.weight"]
-        hi, lo, f = split(wh)
-        self.c.head_w_hi, self.c.head_w_lo, self.c.head_w_f32 = L.ptr(hi), L.ptr(lo), L.ptr(f)
-        self.c.head_b = L.ptr(f32(sd[f"{td}.15.bias"]))
-        self.c.gn_w, self.c.gn_b = L.ptr(f32(sd["norm.weight"])), L.ptr(f32(sd["norm.bias"]))
-        self.c.upd_w, self.c.upd_b = L.ptr(f32(sd["ffeat_updater.0.weight"])), L.ptr(f32(sd["ffeat_updater.0.bias"]))
-        self.c.vis_w, self.c.vis_b = L.ptr(f32(sd["vis_predictor.0.weight"].reshape(-1))), L.ptr(f32(sd["vis_predictor.0.bias"]))
+        split("head_w", wh)
+        f32("head_b", sd[f"{td}.15.bias"])
+        f32("gn_w", sd["norm.weight"])
+        f32("gn_b", sd["norm.bias"])
+        f32("upd_w", sd["ffeat_updater.0.weight"])
+        f32("upd_b", sd["ffeat_updater.0.bias"])
+        f32("vis_w", sd["vis_predictor.0.weight"].reshape(-1))
+        f32("vis_b", sd["vis_predictor.0.bias"])
+        return t
+
+    LAYER_FIELDS = ("ln1_w", "ln1_b", "tok_w1", "tok_b1", "tok_w2", "tok_b2", "ln2_w", "ln2_b",
+                    "fc1_w_hi", "fc1_w_lo", "fc1_w_f32", "fc1_b", "fc2_w_hi", "fc2_w_lo", "fc2_w_f32", "fc2_b")
+    TOP_FIELDS = ("in_w_hi", "in_w_lo", "in_w_f32", "in_b", "out_ln_w", "out_ln_b", "head_w_hi", "head_w_lo",
+                  "head_w_f32", "head_b", "gn_w", "gn_b", "upd_w", "upd_b", "vis_w", "vis_b")
+
+    @classmethod
+    def names(cls):
+        return list(cls.TOP_FIELDS) + [f"layer{l}.{f}" for l in range(L.DEPTH) for f in cls.LAYER_FIELDS]
+
+    def _bind(self) -> None:
+        """Point the C struct at the named tensors (which must stay alive as long as ``self``)."""
+        missing = [n for n in self.names() if n not in self.t]
+        if missing:
+            raise L.PipsCudaError(f"pips_b200: weight pack lacks {missing[:4]}{' ...' if len(missing) > 4 else ''}")
+        for n in self.names():
+            v = self.t[n]
+            if v.device != self.device or not v.is_contiguous():
+                raise L.PipsCudaError(f"pips_b200: weight pack tensor {n} is not a contiguous tensor on {self.device}")
+        for f in self.TOP_FIELDS:
+            setattr(self.c, f, L.ptr(self.t[f]))
+        for l in range(L.DEPTH):
+            for f in self.LAYER_FIELDS:
+                setattr(self.c.layer[l], f, L.ptr(self.t[f"layer{l}.{f}"]))
 
 
 class Workspace:
@@ -181,6 +220,12 @@ class RefineEngine:
             self._weights_key = key
         return self._weights
 
+    def adopt_weights(self, module, packed: PackedWeights) -> None:
+        """Use an already packed weight set (pips_b200/pack.py) for ``module``'s current parameters."""
+        self._plans.clear()
+        self._weights = packed
+        self._weights_key = tuple((p.data_ptr(), p._version) for p in module.parameters())
+
     def workspace(self, seqs: int, device) -> Workspace:
         if self._ws is None or self._ws.seqs < seqs or next(iter(self._ws.keep.values())).device != device:
             self._ws = None
@@ -203,7 +248,8 @@ class RefineEngine:
 
     # ------------------------------------------------------------------ the loop
     def _enqueue(self, lib, wc, pyr: Pyramid, ws: Workspace, fmaps2d, c, c0, ffeat, ffeats, feat_init, out, vis,
-                 B, S, nc, H8, W8, iters, stride, on_iter=None, build_pyramid=True, frame_base=None, T=0) -> int:
+                 B, S, nc, H8, W8, iters, stride, on_iter=None, build_pyramid=True, frame_base=None, T=0,
+                 heat=None, peer=None, peer_n0=0) -> int:
         """Enqueue every launch of one forward for ``nc`` particles on the current stream: pyramid, initial
         features, ``iters`` refinement iterations, visibility head.  Returns the number of kernels launched."""
         st = self._stream()
@@ -228,7 +274,23 @@ class RefineEngine:
         prob.times, prob.coords, prob.coords0, prob.ffeats = L.ptr(self.times(c.device)), L.ptr(c), L.ptr(c0), L.ptr(ffeats)
         prob.stride = float(stride)
         prob.frame_base, prob.frames_per_batch = L.ptr(frame_base), T
+        if heat is not None:
+            sel, slot, fcps = heat                  # local particle indices, output slots, (B,S,I,n_sel_total,H8,W8)
+            scratch = torch.empty(lib.pips_heatmap_scratch_floats(B * S, sel.numel(), H8, W8), dtype=torch.float32,
+                                  device=c.device)
+            lvl_ptrs = L.ptr_array(lvl)
+        if peer is not None:                        # particle-sharded: predictions go straight into every rank's slab
+            prob.peer.n_peers, prob.peer.n_total = peer.slab.world, peer.n_total
+            prob.peer.n_offset = peer.n_offset + peer_n0
         for it in range(iters):
+            if peer is not None:
+                for r, a in enumerate(peer.coord_bases(it)):
+                    prob.peer.out[r] = a
+            if heat is not None:                    # nets/pips.py:502-511: score map of the state the iteration starts from
+                L.check(lib.pips_heatmap(lvl_ptrs, self.feat_dtype, B, S, nc, H8, W8, L.ptr(ffeats), L.ptr(sel), L.ptr(slot),
+                                         sel.numel(), L.ptr(scratch), L.ptr(fcps[0, 0, it]),
+                                         fcps.stride(1), st), "pips_heatmap")
+                launches += 1 + (sel.numel() + 31) // 32
             L.check(lib.pips_refine_iter(C.byref(prob), C.byref(wc), C.byref(ws.c), L.ptr(out[it]), st), "pips_refine_iter")
             launches += 1 + (1 + 3 * L.DEPTH + 2) + 1
             if on_iter is not None:
@@ -238,14 +300,19 @@ class RefineEngine:
 
     def refine(self, module, fmaps: torch.Tensor, coords: torch.Tensor, feat_init: Optional[torch.Tensor],
                iters: int, stride: float, on_iter=None, frame_base: Optional[torch.Tensor] = None,
-               reuse_pyramid: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+               reuse_pyramid: bool = False, heat_sel: Optional[torch.Tensor] = None,
+               heat_out: Optional[torch.Tensor] = None, peer=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """fmaps (B,S,128,H8,W8) fp32, coords (B,S,N,2) fp32 in feature-map pixels.
         Returns preds (iters,B,S,N,2) in input pixels, vis_e (B,S,N) logits, ffeat (B,N,128).
         ``on_iter(it, coords_px)`` (optional) is called once per iteration when the particles fit one
         chunk -- the sharded path hangs its per-iteration all-gather there.
         ``frame_base`` (B,N) int32 (optional): chained tracking -- fmaps then holds T >= 1 frames per batch
         element and track (b,n) works on frames min(frame_base[b,n] + s, T-1), s = 0..7.
-        ``reuse_pyramid``: the pyramid built by the previous call is still valid (same fmaps; chained rounds)."""
+        ``reuse_pyramid``: the pyramid built by the previous call is still valid (same fmaps; chained rounds).
+        ``heat_sel`` (n_sel,) particle indices + ``heat_out`` (B,S,iters,n_sel,H8,W8) fp32: also write the score maps
+        of those particles (nets/pips.py:504-511) at the start of every iteration (eager launches, no graph).
+        ``peer`` (pips_b200.peer.PeerPlan): this call refines one rank's slice of a particle-sharded run; the update
+        kernel also stores every iteration's prediction into all ranks' slabs (the caller runs the barriers)."""
         lib = L.load()
         B, T, Cc, H8, W8 = fmaps.shape
         S = coords.shape[1]
@@ -261,9 +328,17 @@ class RefineEngine:
             fmaps2d = fmaps2d.contiguous()
         chunk = max(1, self.max_seqs // B)
 
-        if N <= chunk and self.use_graph and iters > 0 and frame_base is None:
+        if heat_sel is not None:
+            if frame_base is not None:
+                raise L.PipsCudaError("pips_b200: score maps are not defined for chained windows")
+            heat_sel = heat_sel.to(device=dev, dtype=torch.int32).contiguous()
+            n_sel = heat_sel.numel()
+            assert n_sel > 0 and int(heat_sel.min()) >= 0 and int(heat_sel.max()) < N, "heat_sel out of range"
+            assert heat_out is not None and tuple(heat_out.shape) == (B, S, iters, n_sel, H8, W8) \
+                and heat_out.dtype == torch.float32 and heat_out.is_contiguous() and heat_out.device == dev
+        if N <= chunk and self.use_graph and iters > 0 and frame_base is None and heat_sel is None:
             plan = self._plan(w, B, S, N, H8, W8, iters, float(stride), feat_init is not None, dev,
-                              nhwc=not fmaps2d.is_contiguous())
+                              nhwc=not fmaps2d.is_contiguous(), peer=peer)
             preds, vis, ffeat = plan.run(fmaps2d, coords, feat_init)
             self.launches = plan.launches
             if on_iter is not None:
@@ -289,22 +364,28 @@ class RefineEngine:
             out = preds if whole else torch.empty(iters, B, S, nc, 2, dtype=torch.float32, device=dev)
             v = vis if whole else torch.empty(B, S, nc, dtype=torch.float32, device=dev)
             fb = None if frame_base is None else (frame_base if whole else frame_base[:, n0:n1].contiguous())
+            heat = None
+            if heat_sel is not None:
+                inside = ((heat_sel >= n0) & (heat_sel < n1)).nonzero().flatten()
+                if inside.numel() > 0:
+                    heat = ((heat_sel[inside] - n0).to(torch.int32).contiguous(), inside.to(torch.int32).contiguous(), heat_out)
             self.launches += self._enqueue(lib, w.c, pyr, ws, fmaps2d, c, c0, ffeat, ffeats, fi, out, v, B, S, nc, H8, W8,
                                            iters, stride, on_iter if whole else None,
-                                           build_pyramid=(n0 == 0 and not reuse_pyramid), frame_base=fb, T=T)
+                                           build_pyramid=(n0 == 0 and not reuse_pyramid), frame_base=fb, T=T, heat=heat,
+                                           peer=peer, peer_n0=n0)
             if not whole:
                 preds[:, :, :, n0:n1] = out
                 vis[:, :, n0:n1] = v
             ffeat_out[:, n0:n1] = ffeat.reshape(B, nc, LATENT)
         return preds, vis, ffeat_out
 
-    def _plan(self, w: PackedWeights, B, S, N, H8, W8, iters, stride, has_feat, dev, nhwc=False) -> "_GraphPlan":
-        key = (id(w), B, S, N, H8, W8, iters, stride, has_feat, str(dev), nhwc)
+    def _plan(self, w: PackedWeights, B, S, N, H8, W8, iters, stride, has_feat, dev, nhwc=False, peer=None) -> "_GraphPlan":
+        key = (id(w), B, S, N, H8, W8, iters, stride, has_feat, str(dev), nhwc, None if peer is None else peer.key)
         plan = self._plans.get(key)
         if plan is None:
             while len(self._plans) >= 2:                          # each plan owns a full workspace
                 self._plans.pop(next(iter(self._plans)))
-            plan = _GraphPlan(self, w, B, S, N, H8, W8, iters, stride, has_feat, dev, nhwc)
+            plan = _GraphPlan(self, w, B, S, N, H8, W8, iters, stride, has_feat, dev, nhwc, peer)
             self._plans[key] = plan
         else:
             self._plans[key] = self._plans.pop(key)               # LRU order
@@ -385,9 +466,11 @@ class _GraphPlan:
     with its own static buffers; replayed with new inputs copied in.  ~250 launches per forward collapse
     into one graph launch, which is what matters for small problems (demo / chained windows)."""
 
-    def __init__(self, eng: RefineEngine, w: PackedWeights, B, S, N, H8, W8, iters, stride, has_feat, dev, nhwc=False):
+    def __init__(self, eng: RefineEngine, w: PackedWeights, B, S, N, H8, W8, iters, stride, has_feat, dev, nhwc=False,
+                 peer=None):
         lib = L.load()
         self.w = w
+        self.peer = peer                              # the captured update kernels store into these slabs
         self.iters = iters
         self.pyr = Pyramid(B * S, H8, W8, eng.feat_dtype, dev)
         self.ws = Workspace(B * N, eng.precision, dev)
@@ -408,7 +491,8 @@ class _GraphPlan:
 
         def enqueue():
             return eng._enqueue(lib, w.c, self.pyr, self.ws, self.fmaps_nhwc if nhwc else self.fmaps_nchw, self.c, self.c0,
-                                self.ffeat, self.ffeats, self.feat_in, self.preds, self.vis, B, S, N, H8, W8, iters, stride)
+                                self.ffeat, self.ffeats, self.feat_in, self.preds, self.vis, B, S, N, H8, W8, iters, stride,
+                                peer=peer)
 
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))

@@ -178,6 +178,31 @@ class Pips(nn.Module):
             return self.refine(xys, fmaps, coords_init=coords_init, feat_init=feat_init, iters=iters,
                                return_feat=return_feat)
 
+    @torch.no_grad()
+    def score_maps(self, xys, rgbs, particles, iters=3, coords_init=None, feat_init=None):
+        """The dense score maps ``fcps`` of nets/pips.py:504-511,:565 for the chosen ``particles`` only
+        (SURVEY.md section 8f-3): (B,S,iters,len(particles),H8,W8), i.e. ``fcps[:, :, :, particles]`` of the
+        reference, without the all-pairs volume.  The reference's own consumers look at one particle
+        (``fcps[0:1,:,:,0:1]``, nets/pips.py:572).  Also returns (coord_predictions, vis_e) of the same run."""
+        if not rgbs.is_cuda:
+            raise RuntimeError("pips_b200.Pips.score_maps is CUDA-only (sm_100a)")
+        B, N, D = xys.shape
+        assert (D == 2)
+        S = rgbs.shape[1]
+        fmaps = self.encode(rgbs)
+        stride = float(self.stride)
+        if coords_init is None:
+            coords = (xys.detach().float() / stride).reshape(B, 1, N, 2).repeat(1, S, 1, 1)
+        else:
+            coords = coords_init.detach().float() / stride
+        sel = torch.as_tensor(particles, dtype=torch.int64, device=rgbs.device).flatten()
+        H8, W8 = fmaps.shape[-2:]
+        fcps = torch.empty(B, S, iters, sel.numel(), H8, W8, dtype=torch.float32, device=rgbs.device)
+        preds, vis_e, _ = self._engine.refine(self, fmaps.float(), coords,
+                                              None if feat_init is None else feat_init.detach().float(), iters, stride,
+                                              heat_sel=sel, heat_out=fcps)
+        return fcps, [preds[i] for i in range(iters)], vis_e
+
     def refine(self, xys, fmaps, coords_init=None, feat_init=None, iters=3, return_feat=False):
         """Everything after fnet (nets/pips.py:450-611) given precomputed feature maps."""
         B, N, _ = xys.shape

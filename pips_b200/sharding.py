@@ -37,8 +37,64 @@ def _pad_particles(t: torch.Tensor, dim: int, per: int) -> torch.Tensor:
     return torch.cat([t, last.repeat(*reps)], dim=dim).contiguous()
 
 
+def gather_mode(model) -> str:
+    """'p2p' (peer-mapped slabs, stores fused into the update kernel) or 'nccl' (all-gathers).  Decided once per
+    model: PIPS_B200_GATHER overrides; p2p needs every rank on this host and at most 16 of them."""
+    mode = getattr(model, "_gather_mode", None)
+    if mode is None:
+        import os
+        from . import _lib as L
+        from .peer import same_host
+        _, world, group = model._shard
+        mode = os.environ.get("PIPS_B200_GATHER", "")
+        if mode not in ("p2p", "nccl"):
+            mode = "p2p" if (world <= L.MAX_PEERS and same_host(group)) else "nccl"
+        model._gather_mode = mode
+    return mode
+
+
 def refine_sharded(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_init: Optional[torch.Tensor], iters: int,
                    stride: float):
+    if coords.is_cuda and iters > 0 and gather_mode(model) == "p2p":
+        return refine_sharded_p2p(model, fmaps, coords, feat_init, iters, stride)
+    return refine_sharded_nccl(model, fmaps, coords, feat_init, iters, stride)
+
+
+def refine_sharded_p2p(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_init: Optional[torch.Tensor], iters: int,
+                       stride: float):
+    """No collective on the data path: every rank's update kernel writes its predictions into all ranks' result
+    slabs over NVLink (pips_peer_out), two flag barriers fence the slab's reuse and its completion."""
+    from . import _lib as L
+    from .peer import PeerPlan, PeerSlab
+    rank, world, group = model._shard
+    B, S, N, _ = coords.shape
+    n0, n1, per = shard_bounds(N, rank, world)
+    dev = coords.device
+    need = 4 * PeerPlan.words_needed(world, iters, B, S, per)
+    slab = getattr(model, "_peer_slab", None)
+    if slab is None or slab.nbytes < need or slab.device != dev:           # collective: all ranks see the same shapes
+        if slab is not None:
+            slab.close()
+        model._peer_slab = slab = PeerSlab(max(need, 1 << 22), rank, world, group, dev)
+    plan = PeerPlan(slab, iters, B, S, per)
+    my_coords = _pad_particles(coords[:, :, n0:n1], 2, per)
+    my_feat = None if feat_init is None else _pad_particles(feat_init[:, n0:n1], 1, per)
+
+    slab.barrier()                      # every rank has copied the previous call's results out of its slab
+    _, vis, ffeat = model.engine.refine(model, fmaps, my_coords, my_feat, iters, stride, peer=plan)
+    lib, st = L.load(), torch.cuda.current_stream(dev).cuda_stream
+    vis, ffeat = vis.contiguous(), ffeat.contiguous()
+    L.check(lib.pips_peer_scatter(L.ptr(vis), B * S, per, slab.region_ptrs(plan.off_vis), world, plan.n_total,
+                                  plan.n_offset, st), "pips_peer_scatter")
+    L.check(lib.pips_peer_scatter(L.ptr(ffeat), B, per * ffeat.shape[-1], slab.region_ptrs(plan.off_ffeat), world,
+                                  plan.n_total * ffeat.shape[-1], plan.n_offset * ffeat.shape[-1], st), "pips_peer_scatter")
+    slab.barrier()                      # every rank's stores into this slab have landed
+    c_all, v_all, f_all = plan.views()
+    return c_all[:, :, :, :N].clone(), v_all[:, :, :N].clone(), f_all[:, :N].clone()
+
+
+def refine_sharded_nccl(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_init: Optional[torch.Tensor], iters: int,
+                        stride: float):
     rank, world, group = model._shard
     B, S, N, _ = coords.shape
     n0, n1, per = shard_bounds(N, rank, world)

@@ -35,6 +35,9 @@ CASES = {
 LOSS_CASE = dict(B=2, H=128, W=128, N=9, stride=8, iters=3, head_scale=0.05, seed=6, oob=False, warm=False)
 
 
+FCP_SEL = [0, 4, 7]          # particles whose dense score maps (nets/pips.py:504-511) are recorded for LOSS_CASE
+
+
 def loss_targets(c, xys):
     g = torch.Generator().manual_seed(400 + c["seed"])
     trajs_g = xys[:, None] + torch.cumsum(torch.randn(c["B"], 8, c["N"], 2, generator=g), 1)
@@ -100,8 +103,21 @@ def main():
         model.load_state_dict(sd, strict=True)
         rgbs, xys, extra = case_inputs(c)
         trajs_g, vis_g, valids = loss_targets(c, xys)
-        with torch.no_grad():
-            preds, _, vis_e, losses = model(xys, rgbs, iters=c["iters"], trajs_g=trajs_g, vis_g=vis_g, valids=valids, is_train=is_train)
+        import nets.pips as ref_mod
+        seen, real_loss = {}, ref_mod.score_map_loss
+
+        def spy(fcps, *a, **k):                      # fcps is only visible as this loss's argument (nets/pips.py:603)
+            seen["fcps"] = fcps.detach().clone()
+            return real_loss(fcps, *a, **k)
+
+        ref_mod.score_map_loss = spy
+        try:
+            with torch.no_grad():
+                preds, _, vis_e, losses = model(xys, rgbs, iters=c["iters"], trajs_g=trajs_g, vis_g=vis_g, valids=valids, is_train=is_train)
+        finally:
+            ref_mod.score_map_loss = real_loss
+        if not is_train:
+            out[name + "/fcps_sel"] = seen["fcps"][:, :, :, FCP_SEL].numpy()      # (B,S,I,3,H8,W8)
         out[name + "/preds"] = torch.stack(preds).numpy()
         out[name + "/vis_e"] = vis_e.numpy()
         out[name + "/losses"] = np.array([float(l) for l in losses], dtype=np.float64)

@@ -13,12 +13,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_header_symbols_are_exported():
     hdr = open(os.path.join(ROOT, "include", "pips_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|const char\*)\s+(pips_\w+)\s*\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^(?:int|size_t|const char\*)\s+(pips_\w+)\s*\(", hdr, flags=re.M))
     assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
     lib = L.load()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.pips_abi_version() == 1
+    assert lib.pips_abi_version() == 2
 
 
 def test_argument_validation_without_gpu():

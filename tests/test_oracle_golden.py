@@ -62,3 +62,26 @@ def test_corr_local_equals_allpairs():
 def test_times_axis_is_linspace_0_S():
     t = po.times_axis(8)
     assert t[0] == 0 and t[-1] == 8 and abs(float(t[1]) - 8 / 7) < 1e-6
+
+
+def test_oracle_score_maps_match_reference():
+    """The dense score map fcps (nets/pips.py:504-511) of the oracle against the reference's own, recorded for
+    three particles of the supervised case (captured as the argument of score_map_loss, nets/pips.py:603)."""
+    from tests.golden.make_golden import FCP_SEL, LOSS_CASE
+    c = LOSS_CASE
+    sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+    rgbs, xys, extra = case_inputs(c)
+    traces = []
+    with torch.no_grad():
+        po.forward(sd, xys, rgbs, iters=c["iters"], stride=c["stride"], traces=traces, **extra)
+        x = 2 * (rgbs / 255.0) - 1.0
+        B, S = rgbs.shape[:2]
+        H8, W8 = c["H"] // c["stride"], c["W"] // c["stride"]
+        fmaps = po.fnet(sd, x.reshape(B * S, 3, c["H"], c["W"]), c["stride"]).reshape(B, S, po.LATENT, H8, W8)
+        pyr = po.build_pyramid(fmaps)
+        got = torch.stack([po.heatmap_fcp(po.corr_allpairs(pyr, tr["ffeats_in"]), H8, W8)[:, :, FCP_SEL] for tr in traces], dim=2)
+    ref = GOLD["loss_s8/fcps_sel"]
+    assert got.shape == ref.shape
+    err = np.abs(got.numpy() - ref).max()
+    print("oracle fcps vs reference: max err", err, "|fcps| max", np.abs(ref).max())
+    assert err < 2e-4

@@ -25,15 +25,32 @@ for name, c in CASES.items():
         extra = {"coords_init": (xys[:, None] + torch.cumsum(torch.randn(c["B"], 8, c["N"], 2, generator=g), 1)).to(dev),
                  "feat_init": (torch.randn(c["B"], c["N"], 128, generator=g) * 0.5).to(dev)}
     single = synthetic.seeded_model(stride=c["stride"], seed=3).to(dev).eval()
-    sharded = synthetic.seeded_model(stride=c["stride"], seed=3).to(dev).eval()
-    sharded.shard_particles()
     with torch.no_grad():
         a = single(xys.to(dev), rgbs.to(dev), iters=c["iters"], return_feat=True, **extra)
-        b = sharded(xys.to(dev), rgbs.to(dev), iters=c["iters"], return_feat=True, **extra)
-    same = all(torch.equal(x, y) for x, y in zip(a[0], b[0])) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
-    err = max((x - y).abs().max().item() for x, y in zip(a[0], b[0]))
-    print(f"rank {rank}/{world} {name}: N={c['N']} sharded==single bit-exact: {same} (max diff {err:.2e})", flush=True)
-    ok = ok and same
+    for mode in ("p2p", "nccl"):            # peer-mapped slabs (stores fused into the update kernel) / NCCL all-gathers
+        sharded = synthetic.seeded_model(stride=c["stride"], seed=3).to(dev).eval()
+        sharded.shard_particles()
+        sharded._gather_mode = mode
+        for rep in range(3):                # repeated calls reuse the slab: the barriers must fence it
+            with torch.no_grad():
+                b = sharded(xys.to(dev), rgbs.to(dev), iters=c["iters"], return_feat=True, **extra)
+            same = all(torch.equal(x, y) for x, y in zip(a[0], b[0])) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+            err = max((x - y).abs().max().item() for x, y in zip(a[0], b[0]))
+            ok = ok and same
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0.record()
+        for rep in range(5):
+            with torch.no_grad():
+                sharded(xys.to(dev), rgbs.to(dev), iters=c["iters"], return_feat=True, **extra)
+        t1.record()
+        torch.cuda.synchronize()
+        print(f"rank {rank}/{world} {name} [{mode}]: N={c['N']} sharded==single bit-exact: {same} (max diff {err:.2e}); "
+              f"{t0.elapsed_time(t1) / 5:.2f} ms/forward", flush=True)
+        slab = getattr(sharded, "_peer_slab", None)
+        if slab is not None:
+            slab.close()
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

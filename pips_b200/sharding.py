@@ -73,9 +73,11 @@ def refine_sharded_p2p(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_in
     need = 4 * PeerPlan.words_needed(world, iters, B, S, per)
     slab = getattr(model, "_peer_slab", None)
     if slab is None or slab.nbytes < need or slab.device != dev:           # collective: all ranks see the same shapes
+        grown = 0
         if slab is not None:
+            grown = 2 * slab.nbytes                                         # amortise slowly growing particle counts
             slab.close()
-        model._peer_slab = slab = PeerSlab(max(need, 1 << 22), rank, world, group, dev)
+        model._peer_slab = slab = PeerSlab(max(need, grown, 1 << 16), rank, world, group, dev)
     plan = PeerPlan(slab, iters, B, S, per)
     my_coords = _pad_particles(coords[:, :, n0:n1], 2, per)
     my_feat = None if feat_init is None else _pad_particles(feat_init[:, n0:n1], 1, per)

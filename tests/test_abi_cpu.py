@@ -60,3 +60,44 @@ def test_edge_shapes_are_rejected_by_the_c_abi():
     assert lib.pips_conv_tc(1, 1, 1, 16, 16, 64, 1, 1, 64, 3, 3, 3, 1, 0, 1, 0) != 0         # stride 3
     assert lib.pips_tokenmix(1, 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0) != 0                  # zero sequences
     assert lib.pips_pyramid_build(1, 8, 4, 4, None, None, 0) != 0                            # map too small for 4 levels
+
+
+def test_peer_entry_points_validate_arguments_without_gpu():
+    import ctypes as C
+    lib = L.load()
+    assert lib.pips_peer_scatter(None, 4, 4, None, 2, 8, 0, None) != 0
+    assert b"pips_peer_scatter" in lib.pips_last_error()
+    one = (C.c_void_p * 1)(C.c_void_p(256))
+    assert lib.pips_peer_scatter(C.c_void_p(256), 4, 4, one, 1, 6, 4, None) != 0          # block leaves the row
+    assert b"outside the destination row" in lib.pips_last_error()
+    assert lib.pips_peer_scatter(C.c_void_p(256), 4, 4, one, L.MAX_PEERS + 1, 8, 0, None) != 0
+    assert lib.pips_peer_barrier(one, 1, 1, 1, 1000, None) != 0                            # rank outside n_peers
+    assert b"bad rank" in lib.pips_last_error()
+    assert lib.pips_peer_barrier(one, 0, 1, 1, 0, None) != 0                               # no timeout: could hang a device
+    assert lib.pips_peer_open(None, None) != 0 and lib.pips_peer_close(None) != 0 and lib.pips_peer_free(None) != 0
+    peer = L.PeerOut()
+    peer.n_peers, peer.n_offset, peer.n_total = 2, 6, 8                                     # 6 + N(=4) > 8
+    peer.out[0] = peer.out[1] = 256
+    p = C.c_void_p(256)
+    assert lib.pips_update_peer(p, p, p, p, p, p, p, p, p, 8.0, 1, 8, 4, C.byref(peer), None) != 0
+    assert b"particle slice outside n_total" in lib.pips_last_error()
+
+
+def test_peer_plan_layout():
+    """Slab regions of one forward: disjoint, 8-byte aligned coordinate blocks, sized by words_needed."""
+    from pips_b200.peer import FLAG_WORDS, PeerPlan
+
+    class FakeSlab:
+        world, rank, local = 4, 2, 0x7000000000
+        ptrs = [0x7000000000 + r * (1 << 30) for r in range(4)]
+
+    plan = PeerPlan(FakeSlab(), iters=6, B=4, S=8, per=257)
+    assert plan.n_total == 4 * 257 and plan.n_offset == 2 * 257
+    assert plan.words == PeerPlan.words_needed(4, 6, 4, 8, 257)
+    assert FLAG_WORDS >= L.MAX_PEERS and plan.off_coords == FLAG_WORDS < plan.off_vis < plan.off_ffeat < plan.words
+    bases = [plan.coord_bases(it) for it in range(6)]
+    step = 4 * 4 * 8 * plan.n_total * 2
+    for it in range(6):
+        for r in range(4):
+            assert bases[it][r] == FakeSlab.ptrs[r] + 4 * FLAG_WORDS + it * step and bases[it][r] % 8 == 0
+    assert bases[5][0] + step == FakeSlab.ptrs[0] + 4 * plan.off_vis

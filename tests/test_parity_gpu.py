@@ -163,3 +163,38 @@ def test_demo_configuration_matches_oracle():
     assert err < 1e-3
     assert (vis_e.cpu() - ref[2]).abs().max() < 5e-3
     assert len(preds2) == 10
+
+
+def test_peer_slab_exchange_world1():
+    """The peer-slab result path (update kernel storing into the slab, scatter, flag barrier, slab reuse) with a
+    single rank: same kernels as the multi-GPU run (tools/check_sharded.py covers 2+ GPUs), bit-exact results."""
+    import torch.distributed as dist
+    from pips_b200 import sharding
+    c = CASES["rect_s4_oob"]
+    sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+    model = Pips(S=8, stride=c["stride"]).to(DEV).eval()
+    model.load_state_dict(sd, strict=True)
+    rgbs, xys, _ = case_inputs(c)
+    rgbs, xys = rgbs.to(DEV), xys.to(DEV)
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1)
+    try:
+        with torch.no_grad():
+            fmaps = model.encode(rgbs)
+            coords = (xys / c["stride"]).reshape(xys.shape[0], 1, -1, 2).repeat(1, 8, 1, 1)
+            ref = model.engine.refine(model, fmaps.float(), coords, None, c["iters"], float(c["stride"]))
+            model._shard = (0, 1, None)
+            for _ in range(3):                               # the slab is reused: barriers fence it
+                got = sharding.refine_sharded_p2p(model, fmaps.float(), coords, None, c["iters"], float(c["stride"]))
+                for a, b in zip(ref, got):
+                    assert torch.equal(a, b)
+            big = coords.repeat(1, 1, 40, 1)                 # more particles: the slab grows (collective re-allocation)
+            ref2 = model.engine.refine(model, fmaps.float(), big, None, 2, float(c["stride"]))
+            got2 = sharding.refine_sharded_p2p(model, fmaps.float(), big, None, 2, float(c["stride"]))
+            assert all(torch.equal(a, b) for a, b in zip(ref2, got2))
+        model._peer_slab.close()
+    finally:
+        model._shard = None
+        if created:
+            dist.destroy_process_group()

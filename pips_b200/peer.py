@@ -42,20 +42,40 @@ class PeerSlab:
         self.nbytes = (nbytes + 255) // 256 * 256
         self.epoch = 0
         self.timeout_ms = int(os.environ.get("PIPS_B200_PEER_TIMEOUT_MS", "120000"))
+        # Every step that can fail locally is followed by an exchange of its outcome, so that all ranks either
+        # finish the set-up or raise together (a one-sided failure would leave the others in a collective).
         ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+        self.local, self.ptrs = 0, []
+        err = None
         with torch.cuda.device(device):
-            L.check(lib.pips_peer_alloc(self.nbytes, C.byref(ptr), handle), "pips_peer_alloc")
-            self.local = ptr.value
+            if lib.pips_peer_alloc(self.nbytes, C.byref(ptr), handle) != 0:
+                err = lib.pips_last_error().decode()
+            else:
+                self.local = ptr.value
             handles: List[Optional[bytes]] = [None] * world
-            dist.all_gather_object(handles, handle.raw, group=group)
-            self.ptrs: List[int] = []
-            for r in range(world):
-                if r == rank:
-                    self.ptrs.append(self.local)
-                else:
+            dist.all_gather_object(handles, None if err else handle.raw, group=group)
+            if all(h is not None for h in handles):
+                for r in range(world):
+                    if r == rank:
+                        self.ptrs.append(self.local)
+                        continue
                     p = C.c_void_p()
-                    L.check(lib.pips_peer_open(handles[r], C.byref(p)), "pips_peer_open")
+                    if lib.pips_peer_open(handles[r], C.byref(p)) != 0:
+                        err = lib.pips_last_error().decode()
+                        break
                     self.ptrs.append(p.value)
+            elif err is None:
+                err = "another rank could not allocate its slab"
+            errs: List[Optional[str]] = [None] * world
+            dist.all_gather_object(errs, err, group=group)
+            if any(e is not None for e in errs):
+                for r, p in enumerate(self.ptrs):
+                    if r != rank:
+                        lib.pips_peer_close(p)
+                if self.local:
+                    lib.pips_peer_free(self.local)
+                raise L.PipsCudaError("pips_b200: peer slab set-up failed: " +
+                                      "; ".join(f"rank {r}: {e}" for r, e in enumerate(errs) if e))
         self._keep = _DevPtr(self.local, self.nbytes // 4)
         self.words = torch.as_tensor(self._keep, device=device)            # local slab as a float32 vector
         self._flag_ptrs = (C.c_void_p * world)(*self.ptrs)

@@ -77,7 +77,14 @@ def refine_sharded_p2p(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_in
         if slab is not None:
             grown = 2 * slab.nbytes                                         # amortise slowly growing particle counts
             slab.close()
-        model._peer_slab = slab = PeerSlab(max(need, grown, 1 << 16), rank, world, group, dev)
+        model._peer_slab = None
+        try:
+            model._peer_slab = slab = PeerSlab(max(need, grown, 1 << 16), rank, world, group, dev)
+        except L.PipsCudaError as e:        # raised on every rank together (peer.py): all fall back to NCCL
+            import warnings
+            warnings.warn(f"{e}; exchanging results with NCCL all-gathers instead")
+            model._gather_mode = "nccl"
+            return refine_sharded_nccl(model, fmaps, coords, feat_init, iters, stride)
     plan = PeerPlan(slab, iters, B, S, per)
     my_coords = _pad_particles(coords[:, :, n0:n1], 2, per)
     my_feat = None if feat_init is None else _pad_particles(feat_init[:, n0:n1], 1, per)

@@ -51,13 +51,14 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+    def __init__(self, gpu_index: int, n_gpus: int = 1):
+        # rank 0 watches every GPU of the job (local ranks 0..n-1): the slowest one sets the pace of a sharded step
+        self.idx, self.n, self.proc, self.lines = gpu_index, n_gpus, None, []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
-                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-i", ",".join(str(self.idx + i) for i in range(self.n))], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
         except Exception:
@@ -68,20 +69,27 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, per_gpu, watts = [], [], set(), {}, {}
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
                 sm.append(float(f[1])); mx.append(float(f[2]))
+                per_gpu.setdefault(f[0], []).append(float(f[1]))
+                watts.setdefault(f[0], []).append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        med = {g: statistics.median(v) for g, v in per_gpu.items()}
+        out = {"sm_mhz": min(med.values()) if med else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if len(med) > 1:                     # sm_mhz is the slowest GPU's median
+            out["per_gpu_sm_mhz"] = [med[g] for g in sorted(med, key=int)]
+            out["per_gpu_watts"] = [statistics.median(watts[g]) for g in sorted(watts, key=int)]
+        return out
 
 
 def host_threads() -> int:
@@ -229,7 +237,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(3, args.warmup)):
         step_device()
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(0 if world > 1 else local_rank, world)
     if rank == 0:
         sampler.start()
     t_dev = timed(step_device, args.steps)

@@ -276,3 +276,42 @@ def fnet_tc(enc: Encoder, rgb: torch.Tensor) -> torch.Tensor:
     y = conv_tc(cat, enc.conv2)
     _, AP = _apply_pair(ops, y, ops.stats(y), relu_main=True)
     return conv_tc(AP, enc.conv3, bias=True)
+
+
+# ---- the whole encoder as one CUDA graph per input shape ---------------------------------------------------
+# ~130 launches per call; for few frames (the demo clip, a rank's share of a frame-sharded batch, chained
+# windows) the kernels are microseconds long and the encoder is launch-bound when enqueued one by one.
+
+class _FnetGraph:
+    def __init__(self, enc: Encoder, shape, dtype, dev):
+        self.x = torch.zeros(shape, dtype=dtype, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            fnet_tc(enc, self.x)                          # packs the filters, sets function attributes
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fnet_tc(enc, self.x)
+        self.launches = LAUNCHES[0]
+
+    def run(self, x: torch.Tensor) -> torch.Tensor:
+        self.x.copy_(x)
+        self.graph.replay()
+        LAUNCHES[0] = self.launches
+        return self.out.clone()                           # the static output is overwritten by the next replay
+
+
+def fnet_tc_graphed(enc: Encoder, rgb: torch.Tensor) -> torch.Tensor:
+    """fnet_tc replayed from a CUDA graph captured per (shape, dtype, parameter versions); two plans are kept."""
+    key = (tuple(rgb.shape), rgb.dtype, str(rgb.device), tuple((p.data_ptr(), p._version) for p in enc.parameters()))
+    plans = enc.__dict__.setdefault("_fnet_plans", {})
+    plan = plans.get(key)
+    if plan is None:
+        while len(plans) >= 2:                            # each plan owns every activation of one encoder pass
+            plans.pop(next(iter(plans)))
+        plan = plans[key] = _FnetGraph(enc, rgb.shape, rgb.dtype, rgb.device)
+    else:
+        plans[key] = plans.pop(key)                       # LRU order
+    return plan.run(rgb)

@@ -138,9 +138,10 @@ class Pips(nn.Module):
         infer = rgbs.is_cuda and not torch.is_grad_enabled()
         H8, W8 = H // self.stride, W // self.stride
         if self.fnet_mode == "tc" and infer:
-            from .encoder_fast import fnet_tc
+            from .encoder_fast import fnet_tc, fnet_tc_graphed
             raw = rgbs if rgbs.dtype in (torch.float32, torch.bfloat16) else rgbs.float()
-            f = fnet_tc(self.fnet, raw.reshape(B * S, C, H, W))          # normalisation fused into the stem
+            run = fnet_tc_graphed if self._engine.use_graph else fnet_tc
+            f = run(self.fnet, raw.reshape(B * S, C, H, W).contiguous())  # normalisation fused into the stem
             return f.reshape(B, S, H8, W8, self.latent_dim).permute(0, 1, 4, 2, 3)   # logical (B,S,128,H8,W8)
         x = 2 * (rgbs.float() / 255.0) - 1.0
         if self.fnet_mode == "fast" and infer:

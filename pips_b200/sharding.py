@@ -15,6 +15,16 @@ import torch
 import torch.distributed as dist
 
 
+TRACE = None        # tools/diag_scale.py: a list that receives (label, cuda event) at the phase boundaries of a sharded forward
+
+
+def _mark(label: str) -> None:
+    if TRACE is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        TRACE.append((label, ev))
+
+
 def shard_bounds(N: int, rank: int, world: int) -> Tuple[int, int, int]:
     """Equal-size shards of ceil(N/world) particles (the tail is padded by repeating the last track)."""
     per = (N + world - 1) // world
@@ -89,8 +99,11 @@ def refine_sharded_p2p(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_in
     my_coords = _pad_particles(coords[:, :, n0:n1], 2, per)
     my_feat = None if feat_init is None else _pad_particles(feat_init[:, n0:n1], 1, per)
 
+    _mark("inputs")
     slab.barrier()                      # every rank has copied the previous call's results out of its slab
+    _mark("barrier0")
     _, vis, ffeat = model.engine.refine(model, fmaps, my_coords, my_feat, iters, stride, peer=plan)
+    _mark("refine")
     lib, st = L.load(), torch.cuda.current_stream(dev).cuda_stream
     vis, ffeat = vis.contiguous(), ffeat.contiguous()
     L.check(lib.pips_peer_scatter(L.ptr(vis), B * S, per, slab.region_ptrs(plan.off_vis), world, plan.n_total,
@@ -98,8 +111,11 @@ def refine_sharded_p2p(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_in
     L.check(lib.pips_peer_scatter(L.ptr(ffeat), B, per * ffeat.shape[-1], slab.region_ptrs(plan.off_ffeat), world,
                                   plan.n_total * ffeat.shape[-1], plan.n_offset * ffeat.shape[-1], st), "pips_peer_scatter")
     slab.barrier()                      # every rank's stores into this slab have landed
+    _mark("barrier1")
     c_all, v_all, f_all = plan.views()
-    return c_all[:, :, :, :N].clone(), v_all[:, :, :N].clone(), f_all[:, :N].clone()
+    out = c_all[:, :, :, :N].clone(), v_all[:, :, :N].clone(), f_all[:, :N].clone()
+    _mark("copy_out")
+    return out
 
 
 def refine_sharded_nccl(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_init: Optional[torch.Tensor], iters: int,
@@ -119,7 +135,9 @@ def refine_sharded_nccl(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_i
         out = torch.empty(world * B, S, per, 2, dtype=torch.float32, device=dev)     # concatenated along dim 0
         works.append((dist.all_gather_into_tensor(out, coords_px, group=group, async_op=True), out.view(world, B, S, per, 2), it))
 
+    _mark("inputs")
     preds, vis, ffeat = model.engine.refine(model, fmaps, my_coords, my_feat, iters, stride, on_iter=gather_iter)
+    _mark("refine")
     if len(works) != iters:                      # particles were chunked inside the engine: gather at the end
         works.clear()
         for it in range(iters):
@@ -137,6 +155,7 @@ def refine_sharded_nccl(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_i
     preds_full = gathered.permute(1, 2, 3, 0, 4, 5).reshape(iters, B, S, world * per, 2)[:, :, :, :N].contiguous()
     vis_full = vis_all.permute(1, 2, 0, 3).reshape(B, S, world * per)[:, :, :N].contiguous()
     ff_full = ff_all.permute(1, 0, 2, 3).reshape(B, world * per, -1)[:, :N].contiguous()
+    _mark("gathers")
     return preds_full, vis_full, ff_full
 
 
@@ -151,9 +170,12 @@ def encode_sharded(model, rgbs: torch.Tensor) -> torch.Tensor:
     per = (F_ + world - 1) // world
     flat = rgbs.reshape(F_, C, H, W)
     idx = torch.arange(rank * per, (rank + 1) * per, device=rgbs.device).clamp_(max=F_ - 1)     # tail ranks repeat the last frame
+    _mark("begin")
     mine = model.encode(flat[idx].unsqueeze(0))                                                  # (1, per, 128, H8, W8), NHWC memory
+    _mark("fnet_local")
     H8, W8 = mine.shape[-2:]
     local = mine[0].permute(0, 2, 3, 1).contiguous()                                             # (per, H8, W8, 128)
     full = torch.empty(world * per, H8, W8, local.shape[-1], dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(full, local, group=group)
+    _mark("fmaps_allgather")
     return full[:F_].reshape(B, S, H8, W8, -1).permute(0, 1, 4, 2, 3)                            # logical (B,S,128,H8,W8)

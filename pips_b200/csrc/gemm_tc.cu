@@ -9,7 +9,8 @@
 // 1e-3 px parity target of the refinement loop needs (reference: fp32 nn.Linear,
 // nets/pips.py:104-107,:115,:122).
 //
-// Structure (one CTA per SM, persistent over 128x256 output tiles):
+// Structure (one CTA per SM, persistent over 128 x BN output tiles; BN = 256 for large problems, 128 / 64 when
+// 256-wide tiles would leave most SMs without a tile -- few particles: the demo clip, chained windows):
 //   warp 0      TMA producer   : cp.async.bulk.tensor 128B-swizzled K-chunks of A and W -> smem ring
 //   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (M=128,N=256,K=16) per chunk/term
 //   warp 2      TMEM allocator
@@ -24,26 +25,28 @@
 namespace pips {
 
 constexpr int BM = 128;
-constexpr int BN = 256;
 constexpr int GEMM_THREADS = 384;                 // 4 control warps + 8 epilogue warps
 constexpr uint32_t A_TILE_BYTES = BM * BK * 2;     // 16 KB
-constexpr uint32_t W_TILE_BYTES = BN * BK * 2;     // 32 KB
 
-template <int TERMS>
+template <int TERMS, int BN>
 struct GemmCfg {
+    static constexpr uint32_t kWTileBytes = BN * BK * 2;                  // 32 / 16 / 8 KB
     static constexpr int kOperandCopies = TERMS == 3 ? 2 : 1;             // hi (+ lo)
-    static constexpr uint32_t kStageBytes = kOperandCopies * (A_TILE_BYTES + W_TILE_BYTES);
-    static constexpr int kStages = TERMS == 3 ? 2 : 4;
+    static constexpr uint32_t kStageBytes = kOperandCopies * (A_TILE_BYTES + kWTileBytes);
+    static constexpr uint32_t kFixedBytes = EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kFit = static_cast<int>((227u * 1024u - kFixedBytes) / kStageBytes);
+    static constexpr int kStages = kFit > 8 ? 8 : kFit;                   // x3: 2 / 3 / 4 for BN = 256 / 128 / 64
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int TERMS>
+template <int TERMS, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                const GemmArgs args) {
-    using Cfg = GemmCfg<TERMS>;
+    using Cfg = GemmCfg<TERMS, BN>;
     constexpr int kStages = Cfg::kStages;
+    constexpr uint32_t W_TILE_BYTES = Cfg::kWTileBytes;
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle atoms need 1024-byte alignment
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -178,16 +181,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             float bias[32];
             tmem_ld_32x32(taddr, va);
             load_bias_chunk(args, n0, bias);
+            constexpr int NCH = BN / 64;                         // 32-column chunks per half tile: 4 / 2 / 1
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN / 2; c0 += 64) {
+            for (int c = 0; c < NCH; c += 2) {
+                const int c0 = c * 32;
                 tmem_ld_wait();
-                tmem_ld_32x32(taddr + c0 + 32, vb);
-                epilogue_chunk(args, va, bias, row0, n0 + c0, n0 + c0 + 32, my_stage);
+                if (c + 1 < NCH) tmem_ld_32x32(taddr + c0 + 32, vb);
+                epilogue_chunk(args, va, bias, row0, n0 + c0, c + 1 < NCH ? n0 + c0 + 32 : -1, my_stage);
                 __syncwarp();                                    // tcgen05.ld / wait are warp-collective
-                tmem_ld_wait();
-                if (c0 + 64 < BN / 2) tmem_ld_32x32(taddr + c0 + 64, va);
-                epilogue_chunk(args, vb, bias, row0, n0 + c0 + 32, c0 + 64 < BN / 2 ? n0 + c0 + 64 : -1, my_stage);
-                __syncwarp();
+                if (c + 1 < NCH) {
+                    tmem_ld_wait();
+                    if (c + 2 < NCH) tmem_ld_32x32(taddr + c0 + 64, va);
+                    epilogue_chunk(args, vb, bias, row0, n0 + c0 + 32, c + 2 < NCH ? n0 + c0 + 64 : -1, my_stage);
+                    __syncwarp();
+                }
             }
             tc_fence_before();
             mbar_arrive(tempty0 + 8 * as);
@@ -213,6 +220,18 @@ static bool make_operand_map(CUtensorMap* map, const void* ptr, int rows, int K,
 
 int gemm_tc_pair_dispatch(const void* a_hi, const void* a_lo, int lda, int a_rows, const void* w_hi, const void* w_lo, int ldw,
                           int w_rows, const GemmArgs& args, cudaStream_t st);       // gemm_tc2.cu
+
+// 0: automatic, 1: pair kernel, 64/128/256: single-CTA kernel with that tile width
+static int forced_tile() {
+    const char* e = getenv("PIPS_B200_GEMM_TILE");
+    if (!e || !e[0]) return 0;
+    if (e[0] == 'p') return 1;
+    const int v = atoi(e);
+    return (v == 64 || v == 128 || v == 256) ? v : 0;
+}
+
+int launch_single(int bn, bool x3, const void* a_hi, const void* a_lo, int lda, int a_rows, const void* w_hi, const void* w_lo,
+                  int ldw, int w_rows, const GemmArgs& args, cudaStream_t st);
 
 static bool use_pair_kernel() {
     static int v = -1;
@@ -251,39 +270,70 @@ extern "C" int pips_gemm_tc(const void* a_hi, const void* a_lo, int lda, int a_r
     args.out_f32 = out_f32; args.ldo = ldo;
     args.out_hi = static_cast<__nv_bfloat16*>(out_hi); args.out_lo = static_cast<__nv_bfloat16*>(out_lo); args.ldh = ldh;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // CTA-pair kernel (cta_group::2) whenever the allocations cover whole 256-row pair tiles
-    if (use_pair_kernel() && M > 128 && (a_rows % 256) == 0 && (w_rows % 256) == 0)
+    // Tile shape.  Every variant accumulates each output element over K in the same order (same MMA K-steps, same
+    // hi/lo term order), so the choice changes the schedule, not the bits (tests/test_kernels_gpu.py).
+    //   pair  256x256 per CTA pair (cta_group::2): least operand traffic; needs enough pair tiles to fill the GPU
+    //   128 x {256,128,64} single CTA: when 256-wide tiles would leave most SMs idle (few particles)
+    const int force = forced_tile();                  // PIPS_B200_GEMM_TILE = pair | 256 | 128 | 64 (tests, profiling)
+    const bool pair_ok = use_pair_kernel() && M > 128 && (a_rows % 256) == 0 && (w_rows % 256) == 0;
+    const int pair_tiles = ((M + 255) / 256) * ((N + 255) / 256);
+    const int sms = sm_count();
+    int bn = 256;
+    bool pair = pair_ok && pair_tiles * 2 >= (sms * 3) / 4;          // at least 3/4 of the SMs get a tile
+    if (!pair) {
+        const int tm = (M + BM - 1) / BM;
+        while (bn > 64 && tm * ((N + bn - 1) / bn) < (sms * 3) / 4) bn >>= 1;
+    }
+    if (force == 1) pair = pair_ok;
+    else if (force > 1) { pair = false; bn = force; }
+    if ((w_rows % bn) != 0) { bn = 256; pair = pair && pair_ok; }   // TMA boxes must stay inside the weight allocation
+    if (pair)
         return gemm_tc_pair_dispatch(a_hi, x3 ? a_lo : nullptr, lda, a_rows, w_hi, x3 ? w_lo : nullptr, ldw, w_rows, args, st);
+    return launch_single(bn, x3, a_hi, a_lo, lda, a_rows, w_hi, w_lo, ldw, w_rows, args, st);
+}
+
+namespace pips {
+
+template <int TERMS, int BN>
+static int launch_variant(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mw_hi, const CUtensorMap& mw_lo,
+                          const GemmArgs& args, cudaStream_t st) {
+    using Cfg = GemmCfg<TERMS, BN>;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<TERMS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) return fail_cuda("pips_gemm_tc: smem attribute", e);
+        attr = true;
+    }
+    const int tiles = ((args.M + BM - 1) / BM) * ((args.N + BN - 1) / BN);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    gemm_tc_kernel<TERMS, BN><<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, args);
+    return 0;
+}
+
+int launch_single(int bn, bool x3, const void* a_hi, const void* a_lo, int lda, int a_rows, const void* w_hi, const void* w_lo,
+                  int ldw, int w_rows, const GemmArgs& args, cudaStream_t st) {
+    const int K = args.K;
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     if (!make_operand_map(&ma_hi, a_hi, a_rows, K, lda, BM)) return fail("pips_gemm_tc: tensor map (A hi) failed");
-    if (!make_operand_map(&mw_hi, w_hi, w_rows, K, ldw, BN)) return fail("pips_gemm_tc: tensor map (W hi) failed");
+    if (!make_operand_map(&mw_hi, w_hi, w_rows, K, ldw, bn)) return fail("pips_gemm_tc: tensor map (W hi) failed");
     ma_lo = ma_hi;
     mw_lo = mw_hi;
     if (x3) {
         if (!make_operand_map(&ma_lo, a_lo, a_rows, K, lda, BM)) return fail("pips_gemm_tc: tensor map (A lo) failed");
-        if (!make_operand_map(&mw_lo, w_lo, w_rows, K, ldw, BN)) return fail("pips_gemm_tc: tensor map (W lo) failed");
+        if (!make_operand_map(&mw_lo, w_lo, w_rows, K, ldw, bn)) return fail("pips_gemm_tc: tensor map (W lo) failed");
     }
-    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    const int grid = tiles < sm_count() ? tiles : sm_count();
+    int rc;
+    if (x3) rc = bn == 256 ? launch_variant<3, 256>(ma_hi, ma_lo, mw_hi, mw_lo, args, st)
+               : bn == 128 ? launch_variant<3, 128>(ma_hi, ma_lo, mw_hi, mw_lo, args, st)
+                           : launch_variant<3, 64>(ma_hi, ma_lo, mw_hi, mw_lo, args, st);
+    else rc = bn == 256 ? launch_variant<1, 256>(ma_hi, ma_lo, mw_hi, mw_lo, args, st)
+            : bn == 128 ? launch_variant<1, 128>(ma_hi, ma_lo, mw_hi, mw_lo, args, st)
+                        : launch_variant<1, 64>(ma_hi, ma_lo, mw_hi, mw_lo, args, st);
+    if (rc) return rc;
     cudaError_t e;
-    if (x3) {
-        static bool attr = false;
-        if (!attr) {
-            e = cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<3>::kSmemBytes);
-            if (e != cudaSuccess) return fail_cuda("pips_gemm_tc: smem attribute", e);
-            attr = true;
-        }
-        gemm_tc_kernel<3><<<grid, GEMM_THREADS, GemmCfg<3>::kSmemBytes, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, args);
-    } else {
-        static bool attr = false;
-        if (!attr) {
-            e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::kSmemBytes);
-            if (e != cudaSuccess) return fail_cuda("pips_gemm_tc: smem attribute", e);
-            attr = true;
-        }
-        gemm_tc_kernel<1><<<grid, GEMM_THREADS, GemmCfg<1>::kSmemBytes, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, args);
-    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda("pips_gemm_tc: launch", e);
     return 0;
 }
+
+}  // namespace pips

@@ -177,7 +177,7 @@ def _split(t):
     return hi, lo
 
 
-@pytest.mark.parametrize("pair", [False, True])
+@pytest.mark.parametrize("pair", [False, True, 128, 64])
 @pytest.mark.parametrize("terms", [3, 1])
 @pytest.mark.parametrize("M,N,K,epi", [
     (128, 256, 64, L.EPI_BIAS),            # one tile, one K block
@@ -188,14 +188,16 @@ def _split(t):
     (300, 1040, 512, L.EPI_BIAS),          # head: partial N tile
     (40000, 512, 512, L.EPI_BIAS_RESID),   # > 148 tiles: persistent loop + TMEM double buffering
 ])
-def test_gemm_tc(terms, M, N, K, epi, pair):
-    """pair=True: allocations cover whole 256-row tiles -> the cta_group::2 kernel; False -> single-CTA kernel."""
+def test_gemm_tc(terms, M, N, K, epi, pair, monkeypatch):
+    """pair=True: the cta_group::2 kernel (256x256 per CTA pair); False / 128 / 64: the single-CTA kernel with
+    128 x 256 / 128 / 64 tiles.  The shape is forced -- left alone, pips_gemm_tc picks it from the problem size."""
     lib = L.load()
     torch.manual_seed(7)
+    monkeypatch.setenv("PIPS_B200_GEMM_TILE", "pair" if pair is True else str(pair or 256))
     Ma, Na = (M + 127) // 128 * 128, (N + 255) // 256 * 256
-    if pair:
+    if pair is True:
         Ma = (M + 255) // 256 * 256
-    elif Ma % 256 == 0:
+    elif Ma % 256 == 0 and pair is False:
         Ma += 128
     a = torch.zeros(Ma, K)
     a[:M] = torch.randn(M, K)
@@ -227,6 +229,40 @@ def test_gemm_tc(terms, M, N, K, epi, pair):
         got = of.cpu()
     err = (got - ref).abs().max().item()
     assert err < tol, f"max err {err} (tol {tol})"
+
+
+@pytest.mark.parametrize("terms", [3, 1])
+@pytest.mark.parametrize("M,N,K,epi", [(1000, 2048, 512, L.EPI_BIAS_GELU), (2048, 512, 2048, L.EPI_BIAS_RESID),
+                                       (300, 1040, 512, L.EPI_BIAS)])
+def test_gemm_tile_shapes_are_bit_identical(terms, M, N, K, epi, monkeypatch):
+    """Every tile shape accumulates an output element over K in the same order: the schedule that pips_gemm_tc picks
+    from the problem size (pair / 256 / 128 / 64) must not change a single bit -- particle sharding and chunking,
+    which change M, rely on it."""
+    lib = L.load()
+    torch.manual_seed(5)
+    Ma, Na = (M + 255) // 256 * 256, (N + 255) // 256 * 256
+    a = torch.zeros(Ma, K)
+    a[:M] = torch.randn(M, K)
+    w = torch.zeros(Na, K)
+    w[:N] = torch.randn(N, K) / math.sqrt(K)
+    a_hi, a_lo = (t.to(DEV).contiguous() for t in _split(a))
+    w_hi, w_lo = (t.to(DEV).contiguous() for t in _split(w))
+    bias = torch.randn(N).to(DEV)
+    out0 = torch.randn(M, N)
+    x3 = terms == 3
+    outs = {}
+    for tile in ("pair", "256", "128", "64", ""):                  # "" = automatic choice
+        monkeypatch.setenv("PIPS_B200_GEMM_TILE", tile)
+        of = out0.clone().to(DEV)
+        oh = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+        ol = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+        L.check(lib.pips_gemm_tc(L.ptr(a_hi), L.ptr(a_lo) if x3 else 0, K, Ma, L.ptr(w_hi), L.ptr(w_lo) if x3 else 0, K, Na,
+                                 M, N, K, L.ptr(bias), epi, L.ptr(of), N, L.ptr(oh), L.ptr(ol) if x3 else 0, N, _st()))
+        _sync_check()
+        outs[tile] = (of.cpu(), oh.cpu().view(torch.int16), ol.cpu().view(torch.int16))
+    for tile, o in outs.items():
+        for x, y in zip(o, outs["pair"]):
+            assert torch.equal(x, y), f"tile {tile!r} differs from the pair kernel"
 
 
 @pytest.mark.parametrize("seqs,tc", [(37, False), (37, True), (700, True)])

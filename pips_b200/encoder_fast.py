@@ -57,7 +57,9 @@ class _Ops:
     def stats(self, y: torch.Tensor) -> torch.Tensor:
         N, H, W, C = y.shape
         hw = H * W
-        chunks = max(1, min(16, hw // 64))
+        # partial sums per image: by image size only (never by N: a rank's share of a frame-sharded batch must give
+        # the bits of the whole batch); 64 chunks keep even an 8-frame clip at 512 CTAs
+        chunks = max(1, min(64, hw // 256))
         partial = torch.empty(N, chunks, 2, C, dtype=torch.float32, device=self.dev)
         st = torch.empty(N, 2, C, dtype=torch.float32, device=self.dev)
         L.check(self.lib.pips_inorm_stats(L.ptr(y), N, hw, C, L.ptr(partial), chunks, L.ptr(st), _st()), "pips_inorm_stats")

@@ -47,49 +47,93 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of THIS rank's GPU during the timed region, read through NVML (what nvidia-smi
+    itself reads) from a thread of this process, every 100 ms.  A separate nvidia-smi process polling in a loop
+    attaches to every GPU of the box and was the one thing the device-timed loop had that the e2e loop did not;
+    the in-process query touches only this GPU.  Falls back to an nvidia-smi poller if NVML cannot be loaded."""
+    REASONS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, gpu_index: int, n_gpus: int = 1):
-        # rank 0 watches every GPU of the job (local ranks 0..n-1): the slowest one sets the pace of a sharded step
-        self.idx, self.n, self.proc, self.lines = gpu_index, n_gpus, None, []
+    def __init__(self, device: torch.device):
+        self.device, self.mhz, self.mask, self.max_mhz, self.stop_flag, self.thread, self.smi = device, [], 0, None, False, None, None
+        self.index = device.index or 0
+
+    def _handle(self, nv):
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.device).uuid)
+            return nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            return nv.nvmlDeviceGetHandleByIndex(self.index)
+
+    def _poll(self, nv, h):
+        while not self.stop_flag:
+            try:
+                self.mhz.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.1)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
-                                          "-i", ",".join(str(self.idx + i) for i in range(self.n))], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
-            self.t.start()
+            import pynvml as nv
+            nv.nvmlInit()
+            h = self._handle(nv)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
+            self._start_smi()
 
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm, mx, reasons, per_gpu, watts = [], [], set(), {}, {}
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-                per_gpu.setdefault(f[0], []).append(float(f[1]))
-                watts.setdefault(f[0], []).append(float(f[3]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        med = {g: statistics.median(v) for g, v in per_gpu.items()}
-        out = {"sm_mhz": min(med.values()) if med else None, "sm_max_mhz": max(mx) if mx else None,
-               "reasons": sorted(reasons), "samples": len(sm)}
-        if len(med) > 1:                     # sm_mhz is the slowest GPU's median
-            out["per_gpu_sm_mhz"] = [med[g] for g in sorted(med, key=int)]
-            out["per_gpu_watts"] = [statistics.median(watts[g]) for g in sorted(watts, key=int)]
-        return out
+    def _start_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.smi = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                                         str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.lines = []
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.smi.stdout), daemon=True)
+            self.thread.start()
+        except Exception:
+            self.smi = None
+
+    def stop(self) -> dict:
+        """{"sm_mhz": median, "sm_max_mhz", "reasons": [...], "samples", "source"} for this rank's GPU."""
+        self.stop_flag = True
+        if self.smi is not None:
+            self.smi.terminate()
+            self.thread.join(timeout=2)
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            reasons = set()
+            for ln in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                try:
+                    self.mhz.append(float(f[0])); self.max_mhz = float(f[1])
+                except (ValueError, IndexError):
+                    continue
+                reasons |= {n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")}
+            src = "nvidia-smi"
+        elif self.thread is not None:
+            self.thread.join(timeout=2)
+            reasons = {n for n, bit in self.REASONS.items() if self.mask & bit}
+            src = "nvml"
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0, "source": None}
+        return {"sm_mhz": statistics.median(self.mhz) if self.mhz else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(self.mhz), "source": src}
+
+
+def merge_clocks(per_rank: list) -> dict:
+    """One "clocks" object for the JSON line: the slowest GPU's median sets the pace of a sharded step."""
+    ok = [c for c in per_rank if c and c.get("sm_mhz") is not None]
+    if not ok:
+        return per_rank[0] if per_rank and per_rank[0] else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"]}
+    out = {"sm_mhz": min(c["sm_mhz"] for c in ok), "sm_max_mhz": max(c["sm_max_mhz"] or 0 for c in ok) or None,
+           "reasons": sorted(set().union(*[set(c["reasons"]) for c in ok])), "samples": sum(c["samples"] for c in ok),
+           "source": ok[0]["source"]}
+    if len(per_rank) > 1:
+        out["per_gpu_sm_mhz"] = [c["sm_mhz"] if c else None for c in per_rank]
+    return out
 
 
 def host_threads() -> int:
@@ -237,12 +281,17 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(3, args.warmup)):
         step_device()
     barrier()
-    sampler = ClockSampler(0 if world > 1 else local_rank, world)
-    if rank == 0:
-        sampler.start()
+    sampler = ClockSampler(dev)                      # every rank watches its own GPU
+    sampler.start()
     t_dev = timed(step_device, args.steps)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
+    if world > 1:
+        all_clocks = [None] * world
+        dist.all_gather_object(all_clocks, clocks)
+    else:
+        all_clocks = [clocks]
+    clocks = merge_clocks(all_clocks)
     from pips_b200 import encoder_fast
     launches = (model.engine.launches + (encoder_fast.LAUNCHES[0] if model.fnet_mode == 'tc' else 0)) * args.steps
     step_host()

@@ -167,6 +167,10 @@ class Pips(nn.Module):
             return forward_torch(self, xys, rgbs, coords_init=coords_init, feat_init=feat_init, iters=iters,
                                  trajs_g=trajs_g, vis_g=vis_g, valids=valids, sw=sw, return_feat=return_feat,
                                  is_train=is_train)
+        if N == 0:
+            # the reference fails on an empty particle axis (F.interpolate of the empty correlation volume,
+            # nets/pips.py:509 -> RuntimeError; recorded in tests/golden as edge/n0_error): same error type here
+            raise RuntimeError("pips_b200.Pips: no particles (xys has N = 0); the reference raises here as well")
         if not rgbs.is_cuda:
             raise RuntimeError("pips_b200.Pips: the inference path is CUDA-only (sm_100a); move the model and "
                                "inputs to a CUDA device. There is no CPU fallback.")

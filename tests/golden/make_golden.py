@@ -122,6 +122,15 @@ def main():
         out[name + "/vis_e"] = vis_e.numpy()
         out[name + "/losses"] = np.array([float(l) for l in losses], dtype=np.float64)
         print(name, "losses", out[name + "/losses"])
+    # edge case: no particles.  The reference does not return empty results, it fails -- record how.
+    model = Pips(S=8, stride=8).eval()
+    try:
+        with torch.no_grad():
+            model(torch.zeros(2, 0, 2), torch.zeros(2, 8, 3, 64, 64), iters=2)
+        out["edge/n0_error"] = np.array("none")
+    except Exception as e:                                             # noqa: BLE001
+        out["edge/n0_error"] = np.array(type(e).__name__)
+    print("N = 0 ->", out["edge/n0_error"])
     # chained long-video tracking (chain_demo.py:40-83) with the reference model as the 8-frame tracker
     c = CHAIN_CASE
     sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])

@@ -101,3 +101,15 @@ def test_peer_plan_layout():
         for r in range(4):
             assert bases[it][r] == FakeSlab.ptrs[r] + 4 * FLAG_WORDS + it * step and bases[it][r] % 8 == 0
     assert bases[5][0] + step == FakeSlab.ptrs[0] + 4 * plan.off_vis
+
+
+def test_no_particles_raises_like_the_reference():
+    """N = 0: the reference raises RuntimeError (F.interpolate of the empty volume, nets/pips.py:509; recorded from
+    the unmodified reference by tests/golden/make_golden.py as edge/n0_error); the drop-in raises the same type."""
+    import numpy as np
+    import pytest
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "reference_outputs.npz"))
+    assert str(gold["edge/n0_error"]) == "RuntimeError"
+    model = Pips(S=8, stride=8).eval()
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(2, 0, 2), po.smooth_video(2, 8, 64, 64, seed=1), iters=3)

@@ -85,7 +85,8 @@ def test_strict_fp32_fnet_mode():
     assert np.abs(torch.stack(preds).cpu().numpy() - GOLD["tiny_s8/preds"]).max() < 1e-4
 
 
-@pytest.mark.parametrize("H,W,stride", [(128, 160, 8), (184, 360, 8), (96, 128, 4)])
+@pytest.mark.parametrize("H,W,stride", [(128, 160, 8), (184, 360, 8), (96, 128, 4),
+                                        (100, 130, 8), (90, 122, 4)])      # last two: sizes no stage divides evenly
 def test_fnet_modes_agree(H, W, stride):
     """'fast' (channels-last, fused element-wise kernels, 3xTF32 convs) and 'x3' against strict-fp32 cuDNN."""
     sd = po.init_state_dict(seed=3)

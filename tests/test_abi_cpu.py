@@ -113,3 +113,26 @@ def test_no_particles_raises_like_the_reference():
     model = Pips(S=8, stride=8).eval()
     with pytest.raises(RuntimeError):
         model(torch.zeros(2, 0, 2), po.smooth_video(2, 8, 64, 64, seed=1), iters=3)
+
+
+def test_plain_c_consumer_links_and_struct_layouts_match(tmp_path):
+    """examples/abi_check.c (C99, -Werror) includes the header, links the library without torch and exercises the
+    validation paths; the struct sizes it prints must equal the ctypes mirrors in pips_b200/_lib.py."""
+    import ctypes
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("no gcc")
+    L.load()
+    exe = str(tmp_path / "abi_check")
+    libdir = os.path.join(ROOT, "pips_b200", "lib")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "abi_check.c"), "-L" + libdir, "-lpips_b200", "-Wl,-rpath," + libdir,
+                    "-o", exe], check=True, capture_output=True, text=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "all checks passed" in out, out
+    sizes = dict(re.findall(r"sizeof\((\w+)\)=(\d+)", out))
+    assert int(sizes["pips_weights"]) == ctypes.sizeof(L.Weights)
+    assert int(sizes["pips_workspace"]) == ctypes.sizeof(L.Workspace)
+    assert int(sizes["pips_problem"]) == ctypes.sizeof(L.Problem)

@@ -115,3 +115,30 @@ def test_pack_bind_is_bit_identical(tmp_path):
     with torch.no_grad():
         m3.vis_predictor[0].bias.add_(1.0)
     assert pack.load_pack(m3, os.path.join(d, "model-000000100.pack")) is False
+
+
+def test_pack_is_readable_from_plain_c(tmp_path):
+    """examples/pack_read.c (C99, no dependencies) finds a tensor in the file the Python writer produced."""
+    import re
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "pack_read")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", os.path.join(root, "examples", "pack_read.c"), "-o", exe],
+                   check=True, capture_output=True, text=True)
+    t = _fake_tensors()
+    p = pack.write_tensors(str(tmp_path / "m.pack"), t, "abc", 2)
+    for name in ("mixer.layer3.fc1_w_hi", "mixer.head_b", "mixer.layer11.tok_w2"):
+        out = subprocess.run([exe, p, name], check=True, capture_output=True, text=True).stdout
+        v = t[name]
+        raw = (v.view(torch.int16) if v.dtype == torch.bfloat16 else v).contiguous().numpy().tobytes()
+        h = 1469598103934665603
+        for b in raw:
+            h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        m = re.search(r"dtype=(\w+) shape=(\S+) nbytes=(\d+) fnv1a=([0-9a-f]+)", out)
+        assert m, out
+        assert m.group(1) == str(v.dtype).replace("torch.", "") and m.group(2) == str(list(v.shape)).replace(" ", "")
+        assert int(m.group(3)) == len(raw) and int(m.group(4), 16) == h
+    assert subprocess.run([exe, p, "mixer.nope"], capture_output=True).returncode == 1

@@ -20,6 +20,9 @@ struct GemmArgs {
     __nv_bfloat16* out_hi;       // BIAS_GELU target (row stride ldh); out_lo may be null
     __nv_bfloat16* out_lo;
     int ldh;
+    // CTA-pair kernel only (gemm_tc2.cu): tiles [0, pair_full_tiles) are 256x256; then pair p < pair_narrow_tiles takes
+    // the 256x128 tile p of the remaining 256x256 tiles split in two column halves (0: no narrow tiles)
+    int pair_full_tiles, pair_narrow_tiles;
 };
 
 

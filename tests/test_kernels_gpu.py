@@ -233,7 +233,10 @@ def test_gemm_tc(terms, M, N, K, epi, pair, monkeypatch):
 
 @pytest.mark.parametrize("terms", [3, 1])
 @pytest.mark.parametrize("M,N,K,epi", [(1000, 2048, 512, L.EPI_BIAS_GELU), (2048, 512, 2048, L.EPI_BIAS_RESID),
-                                       (300, 1040, 512, L.EPI_BIAS)])
+                                       (300, 1040, 512, L.EPI_BIAS),
+                                       # partial last wave of the pair kernel -> its 256x128 tail tiles (74 pairs):
+                                       (33000, 512, 512, L.EPI_BIAS_RESID),       # 258 tiles = 3 waves + 36 -> 72 half tiles
+                                       (2400, 2048, 512, L.EPI_BIAS_GELU)])       # 80 tiles = 1 wave + 6 -> 12 half tiles
 def test_gemm_tile_shapes_are_bit_identical(terms, M, N, K, epi, monkeypatch):
     """Every tile shape accumulates an output element over K in the same order: the schedule that pips_gemm_tc picks
     from the problem size (pair / 256 / 128 / 64) must not change a single bit -- particle sharding and chunking,

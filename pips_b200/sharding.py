@@ -2,10 +2,18 @@
 
 Tracks are independent -- the mixer mixes over the S frames and the channels of one track, never
 across particles (nets/pips.py:517-524) -- so rank g refines particles [g*N/G, (g+1)*N/G) against its
-own full copy of the feature pyramid and the only exchange is one small all-gather of the new
-coordinates per iteration (<= 1 MB at the BASELINE configs) plus the visibility logits at the end.
-The gathers are issued asynchronously on NCCL's stream (``async_op=True``): iteration i+1 does not
-depend on them, so they overlap the next iteration's kernels.
+own full copy of the feature pyramid.  The only exchange is the results (every rank returns the full
+``coord_predictions`` / ``vis_e`` / ``ffeat``; <= 1 MB per iteration at the BASELINE configs):
+
+  * ``refine_sharded_p2p`` (default when all ranks share a host): every rank's update kernel stores its slice
+    straight into all ranks' result slabs over NVLink (pips_b200/peer.py, csrc/peer.cu), two flag barriers fence
+    the slab; no collective library call on the data path, everything inside the per-shape CUDA graph;
+  * ``refine_sharded_nccl``: one asynchronous ``all_gather_into_tensor`` per iteration plus two at the end
+    (ranks on different hosts, ``PIPS_B200_GATHER=nccl``, or slab set-up failed -- decided collectively).
+
+``encode_sharded`` splits the encoder's frames over the ranks (one NCCL all-gather of the feature maps).
+Both paths are bit-identical to the unsharded run (tools/check_sharded.py on 2 / 8 GPUs; the host logic is
+covered by the world-size-2 gloo tests in tests/test_sharding_cpu.py).
 """
 from __future__ import annotations
 

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from pips_b200.sharding import encode_sharded, refine_sharded, shard_bounds
+from pips_b200.sharding import encode_sharded, gather_mode, refine_sharded, shard_bounds
 
 
 def test_shard_bounds_cover_all_particles():
@@ -61,6 +61,12 @@ def _worker(rank, world, port, N, use_feat, q):
         rgbs = torch.rand(B, 3, 3, 16, 24)       # 6 frames over 2 ranks; also an odd count: 3 frames
         for clip in (rgbs, rgbs[:1]):
             ok = ok and torch.equal(encode_sharded(model, clip), model.encode(clip))
+        # exchange mode: both ranks on this host -> peer slabs (taken for CUDA tensors only; the CPU tensors above went
+        # through the all-gather path); the environment override wins and is cached per model
+        ok = ok and gather_mode(model) == "p2p"
+        os.environ["PIPS_B200_GATHER"] = "nccl"
+        ok = ok and gather_mode(_FakeModel((rank, world, None))) == "nccl" and gather_mode(model) == "p2p"
+        del os.environ["PIPS_B200_GATHER"]
         q.put((rank, bool(ok), tuple(preds.shape)))
     finally:
         dist.destroy_process_group()

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import pips_oracle as po
-from tests.golden.make_golden import CASES, case_inputs
+from tests.golden.make_golden import CASES, CPU_CASES, case_inputs
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.npz"))
 
@@ -16,10 +16,10 @@ GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_outp
 TOL_PX = 1e-3
 
 
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", list(CASES) + list(CPU_CASES))
 @pytest.mark.parametrize("allpairs", [True, False])
 def test_oracle_matches_reference(name, allpairs):
-    c = CASES[name]
+    c = CASES.get(name) or CPU_CASES[name]
     sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
     rgbs, xys, extra = case_inputs(c)
     with torch.no_grad():

@@ -159,5 +159,35 @@ def main():
     print("wrote", os.path.join(HERE, "reference_outputs.npz"))
 
 
+# BASELINE cfg 2 at full size (the bench workload): B=4, 8 x 384 x 512, N=1024, stride 8, 6 iterations.  Recorded once
+# (minutes of CPU time, ~10 GB of score maps inside the reference) into its own file; stored subsampled to stay small:
+# every iteration's prediction for every 4th particle, the final prediction and the visibility logits for all.
+CFG2_CASE = dict(B=4, H=384, W=512, N=1024, stride=8, iters=6, head_scale=0.05, seed=9, oob=False, warm=False)
+CFG2_EVERY = 4
+
+
+def main_cfg2():
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    from nets.pips import Pips  # the reference, unmodified
+
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    c = CFG2_CASE
+    sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+    model = Pips(S=8, stride=c["stride"]).eval()
+    model.load_state_dict(sd, strict=True)
+    rgbs, xys, _ = case_inputs(c)
+    with torch.no_grad():
+        preds, _, vis_e, ffeat, _ = model(xys, rgbs, iters=c["iters"], return_feat=True)
+    p = torch.stack(preds)                                             # (6, B, S, N, 2)
+    out = {"preds_sub": p[:, :, :, ::CFG2_EVERY].numpy(), "preds_final": p[-1].numpy(), "vis_e": vis_e.numpy(),
+           "ffeat_sub": ffeat[:, ::16].numpy()}
+    np.savez_compressed(os.path.join(HERE, "reference_cfg2.npz"), **out)
+    print("cfg2: mean |d| from init", float((p[-1] - xys[:, None]).abs().mean()), "max", float((p[-1] - xys[:, None]).abs().max()))
+    print("wrote", os.path.join(HERE, "reference_cfg2.npz"), os.path.getsize(os.path.join(HERE, "reference_cfg2.npz")), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if "--cfg2" in sys.argv:
+        main_cfg2()
+    else:
+        main()

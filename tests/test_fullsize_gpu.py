@@ -67,3 +67,29 @@ def test_input_dtype_does_not_matter_for_integer_video(full_run):
         p32, _, _, _ = model(xys[:, :64].contiguous(), rgbs.float(), iters=2)
         p16, _, _, _ = model(xys[:, :64].contiguous(), rgbs, iters=2)
     assert torch.equal(p32[-1], p16[-1])
+
+
+def test_matches_the_reference_recorded_at_full_size():
+    """The unmodified reference was run ONCE on CPU at exactly the bench configuration (B=4, 8x384x512, N=1024, stride 8,
+    6 iterations; tests/golden/make_golden.py --cfg2 -> reference_cfg2.npz, stored subsampled).  Direct comparison of
+    the CUDA path with that recording: no oracle in the loop, the north-star tolerance of 1e-3 px."""
+    import os
+    import numpy as np
+    from tests.golden.make_golden import CFG2_CASE as c, CFG2_EVERY, case_inputs
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_cfg2.npz"))
+    assert (c["B"], c["H"], c["W"], c["N"], c["iters"], c["stride"]) == (B, H, W, N, ITERS, STRIDE)
+    sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+    rgbs, xys, _ = case_inputs(c)
+    model = Pips(S=S, stride=STRIDE).to(DEV).eval()
+    model.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        preds, _, vis_e, ffeat, _ = model(xys.to(DEV), rgbs.to(DEV), iters=ITERS, return_feat=True)
+    p = torch.stack(preds).cpu().numpy()
+    err_iter = np.abs(p[:, :, :, ::CFG2_EVERY] - gold["preds_sub"]).reshape(ITERS, -1).max(1)
+    err_final = np.abs(p[-1] - gold["preds_final"]).max()
+    err_vis = np.abs(vis_e.cpu().numpy() - gold["vis_e"]).max()
+    err_feat = np.abs(ffeat[:, ::16].cpu().numpy() - gold["ffeat_sub"]).max()
+    print(f"cfg2 full size vs reference recording: per-iter max|d trajs| px = {err_iter}, final (all particles) {err_final:.3e}, "
+          f"vis_e {err_vis:.3e}, ffeat {err_feat:.3e}")
+    assert err_iter.max() < 1e-3 and err_final < 1e-3
+    assert err_vis < 5e-3 and err_feat < 5e-4

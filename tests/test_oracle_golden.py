@@ -85,3 +85,20 @@ def test_oracle_score_maps_match_reference():
     err = np.abs(got.numpy() - ref).max()
     print("oracle fcps vs reference: max err", err, "|fcps| max", np.abs(ref).max())
     assert err < 2e-4
+
+
+def test_oracle_matches_reference_at_bench_size():
+    """BASELINE cfg 2 at full size (B=4, 8x384x512, N=1024, 6 iterations): the oracle's local-correlation formulation
+    against the reference recorded once by make_golden.py --cfg2.  About a minute of CPU time."""
+    from tests.golden.make_golden import CFG2_CASE as c, CFG2_EVERY
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_cfg2.npz"))
+    sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+    rgbs, xys, _ = case_inputs(c)
+    with torch.no_grad():
+        preds, _, vis_e, ffeat, _ = po.forward(sd, xys, rgbs, iters=c["iters"], stride=c["stride"], return_feat=True)
+    p = torch.stack(preds).numpy()
+    err = max(np.abs(p[:, :, :, ::CFG2_EVERY] - gold["preds_sub"]).max(), np.abs(p[-1] - gold["preds_final"]).max())
+    print("oracle vs reference at cfg2: max err px", err)
+    assert err < TOL_PX
+    assert np.abs(vis_e.numpy() - gold["vis_e"]).max() < 2e-3
+    assert np.abs(ffeat[:, ::16].numpy() - gold["ffeat_sub"]).max() < 1e-5

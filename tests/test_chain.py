@@ -77,3 +77,57 @@ def test_batched_chain_matches_reference_recording(precision):
     print(f"chain {precision}: {rounds} batched rounds (reference: {sum(len(h) for h in _gold_skips())} model calls), max err {err:.2e} px")
     assert rounds == max(len(h) for h in _gold_skips())
     assert err < 2e-3
+
+
+def test_batched_chain_host_logic_on_cpu():
+    """pips_b200.chain.track_chain with the CUDA engine replaced by the oracle (one 8-frame window per track, selected
+    through ``frame_base`` exactly as pips_corr_gather does: frame min(base + s, T-1)): the batching, the per-track
+    frame offsets, the truncation at the end of the clip, the carried feature and the threshold sweep reproduce the
+    reference's per-particle loop (same skips, same trajectories) -- no GPU involved."""
+    from pips_b200.chain import track_chain
+    c = CHAIN_CASE
+    sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+    rgbs, xy0 = chain_inputs(c)
+    T = rgbs.shape[1]
+    log = []
+
+    class Engine:
+        def refine(self, module, fmaps, coords, feat_init, iters, stride, frame_base=None, reuse_pyramid=False):
+            B, _, na, _ = coords.shape
+            assert B == 1 and fmaps.shape[1] == T and frame_base.shape == (1, na) and frame_base.dtype == torch.int32
+            preds = torch.zeros(iters, 1, 8, na, 2)
+            vis = torch.zeros(1, 8, na)
+            ffeat = torch.zeros(1, na, 128)
+            for n in range(na):
+                idx = (int(frame_base[0, n]) + torch.arange(8)).clamp(max=T - 1)
+                fi = None if feat_init is None else feat_init[:, n:n + 1]
+                with torch.no_grad():
+                    o = po.forward(sd, coords[:, 0, n:n + 1] * stride, torch.zeros(1, 8, 3, c["H"], c["W"]), iters=iters,
+                                   stride=int(stride), fmaps=fmaps[:, idx], feat_init=fi, return_feat=True)
+                preds[:, :, :, n] = torch.stack(o[0])[:, :, :, 0]
+                vis[:, :, n] = o[2][:, :, 0]
+                ffeat[:, n] = o[3][:, 0]
+            log.append(frame_base[0].tolist())
+            return preds, vis, ffeat
+
+    class Model:
+        stride = c["stride"]
+        engine = Engine()
+
+        def encode(self, clip):
+            Bc, Tc = clip.shape[:2]
+            x = 2 * (clip / 255.0) - 1.0
+            with torch.no_grad():
+                f = po.fnet(sd, x.reshape(Bc * Tc, 3, c["H"], c["W"]), c["stride"])
+            return f.reshape(Bc, Tc, 128, c["H"] // c["stride"], c["W"] // c["stride"])
+
+    trajs, rounds = track_chain(Model(), rgbs, xy0, iters=c["iters"], return_rounds=True)
+    gold = _gold_skips()
+    assert rounds == max(len(h) for h in gold)
+    # window starts seen by the engine == cumulative skips of the reference, per surviving track
+    starts = [[0] + list(np.cumsum(h)[:-1]) for h in gold]
+    for r, bases in enumerate(log):
+        assert bases == [s[r] for s in starts if len(s) > r]
+    err = np.abs(trajs.numpy() - GOLD["chain/trajs"]).max()
+    print("batched chain host logic (oracle windows) vs reference recording: max err px", err)
+    assert err < 1e-3

@@ -43,9 +43,14 @@ def pick_skip(vis: torch.Tensor, thr_table: torch.Tensor) -> torch.Tensor:
 
 
 @torch.no_grad()
-def track_chain(model, rgbs: torch.Tensor, xy0: torch.Tensor, iters: int = 6, return_rounds: bool = False):
+def track_chain(model, rgbs: torch.Tensor, xy0: torch.Tensor, iters: int = 6, return_rounds: bool = False,
+                advance: Optional[int] = None):
     """rgbs (1, T, 3, H, W) float 0..255, xy0 (1, N, 2) start positions at frame 0 (input pixels).
-    Returns trajs_e (1, T, N, 2).  Equivalent to chain_demo.py:run_model's per-particle loop."""
+    Returns trajs_e (1, T, N, 2).  Equivalent to chain_demo.py:run_model's per-particle loop.
+    ``advance`` (2..7): every track moves on by that many frames per round instead of the visibility-driven
+    choice -- a data-independent schedule (ceil((T-1)/advance) rounds) for throughput measurements."""
+    if advance is not None and not 2 <= int(advance) <= S_WIN - 1:
+        raise ValueError("advance must be in 2..7 (the reference's sweep never picks another frame, chain_demo.py:63-76)")
     B, T, C, H, W = rgbs.shape
     assert B == 1, "chained tracking follows the reference: one clip at a time"
     N = xy0.shape[1]
@@ -78,7 +83,7 @@ def track_chain(model, rgbs: torch.Tensor, xy0: torch.Tensor, iters: int = 6, re
         t_idx = base.view(1, na) + torch.arange(S_WIN, device=dev).view(S_WIN, 1)    # (8, na)
         ok = t_idx < T                                                               # S_local truncation, :61
         traj[t_idx[ok], active.view(1, na).expand(S_WIN, na)[ok]] = xys[ok]
-        si = pick_skip(torch.sigmoid(vis_e[0]), thr)
+        si = pick_skip(torch.sigmoid(vis_e[0]), thr) if advance is None else torch.full_like(base, int(advance))
         cur[active] = base + si
         active = active[cur[active] < T]
         rounds += 1

@@ -131,3 +131,31 @@ def test_batched_chain_host_logic_on_cpu():
     err = np.abs(trajs.numpy() - GOLD["chain/trajs"]).max()
     print("batched chain host logic (oracle windows) vs reference recording: max err px", err)
     assert err < 1e-3
+
+
+def test_fixed_advance_schedule_is_data_independent():
+    """advance=7: ceil((T-1)/7) rounds, every track in every round, window starts 0, 7, 14, ..."""
+    from pips_b200.chain import track_chain
+    T, N = 30, 6
+    seen = []
+
+    class Engine:
+        def refine(self, module, fmaps, coords, feat_init, iters, stride, frame_base=None, reuse_pyramid=False):
+            na = coords.shape[2]
+            seen.append(frame_base[0].tolist())
+            preds = (coords * stride).unsqueeze(0).repeat(iters, 1, 1, 1, 1) + 1.0
+            return preds, torch.full((1, 8, na), -10.0), torch.zeros(1, na, 128)      # "invisible": the sweep would lower thr
+
+    class Model:
+        stride = 4
+        engine = Engine()
+
+        def encode(self, clip):
+            return torch.zeros(clip.shape[0], clip.shape[1], 128, 4, 4)
+
+    trajs, rounds = track_chain(Model(), torch.zeros(1, T, 3, 16, 16), torch.rand(1, N, 2) * 16, iters=2, return_rounds=True,
+                                advance=7)
+    assert rounds == 5 and seen == [[7 * r] * N for r in range(5)]
+    assert trajs.shape == (1, T, N, 2) and bool(torch.isfinite(trajs).all())
+    with pytest.raises(ValueError):
+        track_chain(Model(), torch.zeros(1, T, 3, 16, 16), torch.rand(1, N, 2), advance=1)

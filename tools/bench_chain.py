@@ -19,3 +19,13 @@ torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 print(f"chain cfg5: T={T} {H}x{W} N={N} stride 4: {rounds} batched rounds, {dt*1e3:.1f} ms wall, "
       f"{T*N/dt:.0f} tracked particle-frames/s; finite={bool(torch.isfinite(trajs).all())}")
+
+# data-independent schedule (fixed advance 7: ceil((T-1)/7) rounds) -- the throughput figure of SURVEY.md section 8d
+for _ in range(2):
+    track_chain(model, rgbs, xy0, iters=6, advance=7)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+trajs, rounds = track_chain(model, rgbs, xy0, iters=6, return_rounds=True, advance=7)
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+print(f"chain cfg5, fixed advance 7: {rounds} rounds, {dt*1e3:.1f} ms wall, {T*N/dt:.0f} tracked particle-frames/s")

@@ -181,6 +181,12 @@ def make_oracle_inputs():
 
 
 # ------------------------------------------------------------------------------------------ reference arm
+def workload_name(world: int) -> str:
+    """config.workload of BOTH arms: the BASELINE configuration the metric is quoted on."""
+    return (f"BASELINE cfg2 per GPU: B={B}, S={S}, {H}x{W} bf16 video, N={N_PER_GPU}/GPU (global N={N_PER_GPU * world}), "
+            f"iters={ITERS}, stride={STRIDE}")
+
+
 def run_reference(args, rank, world):
     """The reference's algorithm (all-pairs volume, dense heat-map, fp32 torch ops -- nets/pips.py:428-611
     restated in oracle/pips_oracle.py; the reference itself is Python and cannot travel to the GPU box) on
@@ -213,7 +219,7 @@ def run_reference(args, rank, world):
     sample = f"B={bs} of {B}, N={ns} of {N_PER_GPU}, iters={ITERS}, incl. fnet, all-pairs volume + dense heat-map as the reference computes them"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"cfg2 sample: {sample}", "stride": STRIDE},
+            "config": {"workload": workload_name(world), "sample_per_step": sample, "stride": STRIDE},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
@@ -365,7 +371,7 @@ def run_ours(args, rank, world, local_rank):
             "warmup": max(3, args.warmup), "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (hi/lo split, fp32 accumulate) + f32", "bf16": "bf16"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": f"BASELINE cfg2 per GPU: B={B}, S={S}, {H}x{W} bf16 video, N={N_PER_GPU}/GPU (global N={n_global}), iters={ITERS}, stride={STRIDE}",
+            "config": {"workload": workload_name(world),
                        "precision": args.precision, "feat_dtype": args.feat, "parallelism": f"particle-sharded dp{world}" if world > 1 else "single GPU",
                        "includes": "fnet (tcgen05 convs) + pyramid + 6 refinement iterations + vis head", "fnet_mode": model.fnet_mode, "l2": "256 MB write between steps (L2 flushed); working set > L2"},
             "clocks": clocks, "gpu_launches": launches,

@@ -186,8 +186,95 @@ def main_cfg2():
     print("wrote", os.path.join(HERE, "reference_cfg2.npz"), os.path.getsize(os.path.join(HERE, "reference_cfg2.npz")), "bytes")
 
 
+# BASELINE cfg 4 shape: B=1, 8 x 720 x 1280, stride 8 (90 x 160 maps -> 45x80 -> 22x40 -> 11x20), N=16384 queries, 6 iterations.
+# The reference cannot hold the all-pairs volume for 16384 particles (10 GB per iteration); its own recipe for many
+# particles is to run them in chunks of 256 (test_on_davis.py:111-125).  Particles are independent (nets/pips.py:517-524),
+# so ONE such chunk -- every 64th query of the 16384 -- pins the CUDA path at this shape: the GPU test tracks all 16384
+# and compares those 256.
+CFG4_CASE = dict(B=1, H=720, W=1280, N=16384, stride=8, iters=6, head_scale=0.05, seed=10, oob=False, warm=False)
+CFG4_EVERY = 64
+
+
+def main_cfg4():
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    from nets.pips import Pips  # the reference, unmodified
+
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    c = CFG4_CASE
+    sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+    model = Pips(S=8, stride=c["stride"]).eval()
+    model.load_state_dict(sd, strict=True)
+    rgbs, xys, _ = case_inputs(c)
+    chunk = xys[:, ::CFG4_EVERY].contiguous()                          # (1, 256, 2)
+    assert chunk.shape[1] == 256
+    with torch.no_grad():
+        preds, _, vis_e, ffeat, _ = model(chunk, rgbs, iters=c["iters"], return_feat=True)
+    p = torch.stack(preds)
+    out = {"preds": p.numpy(), "vis_e": vis_e.numpy(), "ffeat": ffeat.numpy()}
+    np.savez_compressed(os.path.join(HERE, "reference_cfg4.npz"), **out)
+    print("cfg4 chunk: mean |d| from init", float((p[-1] - chunk[:, None]).abs().mean()), "max", float((p[-1] - chunk[:, None]).abs().max()))
+    print("wrote", os.path.join(HERE, "reference_cfg4.npz"), os.path.getsize(os.path.join(HERE, "reference_cfg4.npz")), "bytes")
+
+
+# BASELINE cfg 1 on the REAL demo clip: /root/reference/demo_images/000100-000107.jpg decoded with PIL, the recipe of
+# demo.py:21-41 (float, bilinear resize to 360 x 640, 16 x 16 query grid with an 8 px margin, model(xy, rgbs, iters=6)),
+# stride 4 as demo.py:114.  The eight JPEG files (320 KB) are stored inside the fixture together with the SHA-256 of the
+# decoded pixels, so that the test on the GPU box -- where /root/reference does not exist -- feeds the same bytes.
+DEMO_CASE = dict(B=1, H=360, W=640, N=256, stride=4, iters=6, head_scale=0.05, seed=11)
+DEMO_FRAMES = list(range(100, 108))
+
+
+def demo_decode(jpeg_blobs):
+    """list of JPEG byte strings -> (1, S, 3, H, W) float tensor 0..255 (demo.py:134-144 reads with imageio == PIL decode)."""
+    import io
+    from PIL import Image
+    fr = [np.array(Image.open(io.BytesIO(bytes(b))).convert("RGB")) for b in jpeg_blobs]
+    return torch.from_numpy(np.stack(fr)).permute(0, 3, 1, 2).unsqueeze(0).float()
+
+
+def demo_inputs(rgbs):
+    """demo.py:21-36: resize to 360 x 640, 16 x 16 grid of queries (utils.basic.meshgrid2d order: y outer, x inner)."""
+    import torch.nn.functional as F
+    Bq, S, C, H, W = rgbs.shape
+    H_, W_ = 360, 640
+    rgbs = F.interpolate(rgbs.reshape(Bq * S, C, H, W), (H_, W_), mode="bilinear").reshape(Bq, S, C, H_, W_)
+    N_ = 16
+    gy, gx = torch.meshgrid(torch.arange(N_).float(), torch.arange(N_).float(), indexing="ij")
+    gy = 8 + gy.reshape(Bq, -1) / float(N_ - 1) * (H_ - 16)
+    gx = 8 + gx.reshape(Bq, -1) / float(N_ - 1) * (W_ - 16)
+    return rgbs, torch.stack([gx, gy], dim=-1)
+
+
+def main_demo():
+    import hashlib
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    from nets.pips import Pips  # the reference, unmodified
+
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    c = DEMO_CASE
+    blobs = [open(f"/root/reference/demo_images/{i:06d}.jpg", "rb").read() for i in DEMO_FRAMES]
+    raw = demo_decode(blobs)
+    rgbs, xy = demo_inputs(raw)
+    sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+    model = Pips(S=8, stride=c["stride"]).eval()
+    model.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        preds, preds2, vis_e, ffeat, _ = model(xy, rgbs, iters=c["iters"], return_feat=True)
+    p = torch.stack(preds)
+    out = {f"jpeg{i}": np.frombuffer(b, dtype=np.uint8) for i, b in enumerate(blobs)}
+    out["pixels_sha256"] = np.array(hashlib.sha256(raw.to(torch.uint8).numpy().tobytes()).hexdigest())
+    out.update({"preds": p.numpy(), "vis_e": vis_e.numpy(), "ffeat": ffeat.numpy()})
+    np.savez_compressed(os.path.join(HERE, "reference_demo.npz"), **out)
+    print("demo clip: mean |d| from init", float((p[-1] - xy[:, None]).abs().mean()), "max", float((p[-1] - xy[:, None]).abs().max()))
+    print("wrote", os.path.join(HERE, "reference_demo.npz"), os.path.getsize(os.path.join(HERE, "reference_demo.npz")), "bytes")
+
+
 if __name__ == "__main__":
     if "--cfg2" in sys.argv:
         main_cfg2()
+    elif "--cfg4" in sys.argv:
+        main_cfg4()
+    elif "--demo" in sys.argv:
+        main_demo()
     else:
         main()

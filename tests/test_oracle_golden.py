@@ -102,3 +102,40 @@ def test_oracle_matches_reference_at_bench_size():
     assert err < TOL_PX
     assert np.abs(vis_e.numpy() - gold["vis_e"]).max() < 2e-3
     assert np.abs(ffeat[:, ::16].numpy() - gold["ffeat_sub"]).max() < 1e-5
+
+
+def test_oracle_matches_reference_on_the_real_demo_clip():
+    """BASELINE cfg 1 on the real frames demo_images/000100-000107.jpg (stored as JPEG bytes inside the fixture), the
+    recipe of demo.py:21-41 (16 x 16 grid, 360 x 640, stride 4, 6 iterations): oracle against the reference's recording."""
+    import hashlib
+    from tests.golden.make_golden import DEMO_CASE as c, demo_decode, demo_inputs
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_demo.npz"))
+    raw = demo_decode([gold[f"jpeg{i}"].tobytes() for i in range(8)])
+    if hashlib.sha256(raw.to(torch.uint8).numpy().tobytes()).hexdigest() != str(gold["pixels_sha256"]):
+        pytest.skip("this host's JPEG decoder produces different pixels than the one the fixture was recorded with")
+    rgbs, xy = demo_inputs(raw)
+    sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+    with torch.no_grad():
+        preds, _, vis_e, ffeat, _ = po.forward(sd, xy, rgbs, iters=c["iters"], stride=c["stride"], return_feat=True)
+    err = np.abs(torch.stack(preds).numpy() - gold["preds"]).max()
+    print("oracle vs reference on the demo clip: max err px", err)
+    assert err < TOL_PX
+    assert np.abs(vis_e.numpy() - gold["vis_e"]).max() < 2e-3
+    assert np.abs(ffeat.numpy() - gold["ffeat"]).max() < 1e-5
+
+
+def test_oracle_matches_reference_at_cfg4_shape():
+    """BASELINE cfg 4 shape (8 x 720 x 1280, stride 8 -> 90 x 160 maps): the 256-particle chunk the reference was run on
+    (every 64th of the 16384 queries; test_on_davis.py:111-125 chunks the same way)."""
+    from tests.golden.make_golden import CFG4_CASE as c, CFG4_EVERY
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_cfg4.npz"))
+    sd = po.init_state_dict(seed=c["seed"], head_scale=c["head_scale"])
+    rgbs, xys, _ = case_inputs(c)
+    with torch.no_grad():
+        preds, _, vis_e, ffeat, _ = po.forward(sd, xys[:, ::CFG4_EVERY].contiguous(), rgbs, iters=c["iters"], stride=c["stride"],
+                                               return_feat=True)
+    err = np.abs(torch.stack(preds).numpy() - gold["preds"]).max()
+    print("oracle vs reference at the cfg4 shape: max err px", err)
+    assert err < TOL_PX
+    assert np.abs(vis_e.numpy() - gold["vis_e"]).max() < 2e-3
+    assert np.abs(ffeat.numpy() - gold["ffeat"]).max() < 1e-5

@@ -19,6 +19,36 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr"]
 
 
+DIGEST = LIB + ".digest"
+
+
+def source_digest() -> str:
+    """SHA-256 over every source, header and the compiler flags: what the built library was made from.
+    Robust to mtime churn (the repo snapshot pushed to the GPU box keeps contents, not necessarily times)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    files.append(os.path.join(os.path.dirname(HERE), "include", "pips_b200.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def is_stale() -> bool:
+    """True when libpips_b200.so is missing or was built from other sources than the ones on disk."""
+    if not os.path.exists(LIB) or not os.path.exists(DIGEST):
+        return True
+    with open(DIGEST) as f:
+        return f.read().strip() != source_digest()
+
+
+def have_nvcc() -> bool:
+    import shutil
+    return any(c and (os.path.exists(c) if os.path.isabs(c) else shutil.which(c)) for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"))
+
+
 def _nvcc() -> str:
     for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
@@ -46,6 +76,8 @@ def _compile(src: str, log: list) -> str:
 
 
 def build(verbose: bool = False, force: bool = False) -> str:
+    if not force and not is_stale():
+        return LIB
     os.makedirs(OBJ, exist_ok=True)
     if force:
         for f in os.listdir(OBJ):
@@ -58,6 +90,8 @@ def build(verbose: bool = False, force: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(DIGEST, "w") as f:
+        f.write(source_digest() + "\n")
     if verbose:
         for src, err in log:
             print(f"--- {src}\n{err}", file=sys.stderr)

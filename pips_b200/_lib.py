@@ -114,10 +114,17 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = lib_path()
-    if not os.path.exists(path):
-        if not build_if_missing:
+    if _build.is_stale():
+        # missing, or built from other sources than the ones on disk (content digest, not mtimes)
+        multi = int(os.environ.get("WORLD_SIZE", "1")) > 1           # ranks of one torchrun must not race on the link step
+        if build_if_missing and _build.have_nvcc() and not (multi and os.path.exists(path)):
+            _build.build()
+        elif not os.path.exists(path):
             raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
-        _build.build()
+        else:
+            import warnings
+            warnings.warn(f"{path} was built from different sources than pips_b200/csrc now holds; "
+                          "rebuild with `python -c 'import __graft_entry__ as g; g.build()'`")
     lib = C.CDLL(path)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here == missing export: fail loudly

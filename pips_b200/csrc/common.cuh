@@ -13,7 +13,20 @@ namespace pips {
 int fail(const char* msg);
 int fail_cuda(const char* where, cudaError_t e);
 
-int sm_count();
+int sm_count();          // of the CURRENT device (cached per device)
+
+// Opt-in to > 48 KB of dynamic shared memory.  cudaFuncSetAttribute applies to the current device only, so the
+// "already done" flag is kept per device (a process that drives several GPUs -- nn.DataParallel -- needs it on each).
+constexpr int kMaxDevices = 64;
+int current_device();
+template <typename F>
+inline cudaError_t ensure_dyn_smem(F* func, bool (&done)[kMaxDevices], int bytes) {
+    const int dev = current_device();
+    if (dev >= 0 && dev < kMaxDevices && done[dev]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < kMaxDevices) done[dev] = true;
+    return e;
+}
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda,
 // so it also loads on a machine without a driver -- the CPU-side ABI tests rely on that).

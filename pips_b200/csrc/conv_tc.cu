@@ -255,11 +255,10 @@ static int conv_tc_impl(const void* x_hi, const void* x_lo, int N, int H, int W,
             !encode_tiled(&mw_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w_lo), gdim, gstr, box, estr, CU_TENSOR_MAP_SWIZZLE_128B))
             return fail("pips_conv_tc: weight tensor map failed");
     }
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM_BYTES);
+    static bool attr[kMaxDevices] = {};
+    {
+        cudaError_t e = ensure_dyn_smem(conv_tc_kernel, attr, C_SMEM_BYTES);
         if (e != cudaSuccess) return fail_cuda("pips_conv_tc: smem attribute", e);
-        attr = true;
     }
     const int total_tiles = N * a.tiles_x * a.tiles_y;
     const int pair_tiles = (total_tiles + 1) / 2;

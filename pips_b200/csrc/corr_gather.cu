@@ -266,11 +266,10 @@ static int launch_corr_gather(const void* const* lvl, CUtensorMapDataType dt, co
             return fail("pips_corr_gather: cuTensorMapEncodeTiled failed");
     }
     using Cfg = CgCfg<T>;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(corr_gather_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(Cfg::kSmemBytes));
+    static bool attr[kMaxDevices] = {};
+    {
+        cudaError_t e = ensure_dyn_smem(corr_gather_kernel<T>, attr, static_cast<int>(Cfg::kSmemBytes));
         if (e != cudaSuccess) return fail_cuda("pips_corr_gather: smem attribute", e);
-        attr = true;
     }
     const long long units = static_cast<long long>(args.B) * args.S * args.N;
     const int ctas_per_sm = sizeof(T) == 2 ? 2 : 1;

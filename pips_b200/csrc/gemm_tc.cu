@@ -298,11 +298,10 @@ template <int TERMS, int BN>
 static int launch_variant(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mw_hi, const CUtensorMap& mw_lo,
                           const GemmArgs& args, cudaStream_t st) {
     using Cfg = GemmCfg<TERMS, BN>;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<TERMS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    static bool attr[kMaxDevices] = {};
+    {
+        cudaError_t e = ensure_dyn_smem(gemm_tc_kernel<TERMS, BN>, attr, Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail_cuda("pips_gemm_tc: smem attribute", e);
-        attr = true;
     }
     const int tiles = ((args.M + BM - 1) / BM) * ((args.N + BN - 1) / BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();

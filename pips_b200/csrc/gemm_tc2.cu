@@ -244,11 +244,10 @@ template <int TERMS>
 static int launch_pair(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mw_hi, const CUtensorMap& mw_lo,
                        const CUtensorMap& mwn_hi, const CUtensorMap& mwn_lo, GemmArgs args, cudaStream_t st) {
     using Cfg = PairCfg<TERMS>;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    static bool attr[kMaxDevices] = {};
+    {
+        cudaError_t e = ensure_dyn_smem(gemm_tc2_kernel<TERMS>, attr, Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail_cuda("pips_gemm_tc (pair): smem attribute", e);
-        attr = true;
     }
     const int tiles = ((args.M + P_BM - 1) / P_BM) * ((args.N + P_BN - 1) / P_BN);
     const int max_pairs = sm_count() / 2;

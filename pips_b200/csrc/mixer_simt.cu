@@ -356,11 +356,10 @@ extern "C" int pips_update_peer(const float* delta, float* coords, const float* 
     if (B <= 0 || N <= 0) return fail("pips_update: empty problem");
     const int rows = B * N * S;
     const size_t smem = (128 * 129 + UP_ROWS * 132) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    static bool attr[kMaxDevices] = {};
+    {
+        cudaError_t e = ensure_dyn_smem(update_kernel, attr, static_cast<int>(smem));
         if (e != cudaSuccess) return fail_cuda("pips_update: smem attribute", e);
-        attr = true;
     }
     update_kernel<<<(rows + UP_ROWS - 1) / UP_ROWS, 256, smem, static_cast<cudaStream_t>(stream)>>>(
         delta, coords, coords0, ffeats, gn_w, gn_b, wu, bu, out_px, stride, B, S, N, po);

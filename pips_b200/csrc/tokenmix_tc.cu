@@ -222,11 +222,10 @@ using namespace pips;
 // called by pips_tokenmix (mixer_simt.cu) for the bf16 / bf16x3 precisions
 int tokenmix_tc_launch(float* x, int seqs, const float* ln1_w, const float* ln1_b, const float* w1, const float* b1, const float* w2,
                        const float* b2, const float* ln2_w, const float* ln2_b, void* y_hi, void* y_lo, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(tokenmix_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TT_SMEM));
+    static bool attr[kMaxDevices] = {};
+    {
+        cudaError_t e = ensure_dyn_smem(tokenmix_tc_kernel, attr, static_cast<int>(TT_SMEM));
         if (e != cudaSuccess) return fail_cuda("pips_tokenmix (tc): smem attribute", e);
-        attr = true;
     }
     const int cap = 2 * sm_count();
     const int grid = seqs < cap ? seqs : cap;

@@ -220,14 +220,16 @@ def adopt_filter(enc: Encoder, name: str, conv: torch.nn.Conv2d, hi: torch.Tenso
     key = (w.data_ptr(), w._version)
     if conv is enc.conv1:
         expect = (64, 7 * 64)
-        conv._wstem, conv._wstem_key = (hi, lo), key
     else:
         cout, cin, R, S = w.shape
         bn = 64 if cout <= 64 else (128 if cout <= 128 else 256)
         expect = (bn, R * S * _pad64(cin))
-        conv._wtc, conv._wtc_key = (hi, lo), key
     if tuple(hi.shape) != expect or tuple(lo.shape) != expect or hi.dtype != torch.bfloat16 or hi.device != w.device:
         raise L.PipsCudaError(f"pips_b200: packed filter {name} has shape {tuple(hi.shape)}, expected {expect}")
+    if conv is enc.conv1:                                   # validated: only now does it become the cache entry
+        conv._wstem, conv._wstem_key = (hi, lo), key
+    else:
+        conv._wtc, conv._wtc_key = (hi, lo), key
 
 
 def fnet_tc(enc: Encoder, rgb: torch.Tensor) -> torch.Tensor:

@@ -220,6 +220,15 @@ class RefineEngine:
             self._weights_key = key
         return self._weights
 
+    def invalidate(self, graphs_only: bool = False) -> None:
+        """Drop the captured CUDA graphs (and, unless ``graphs_only``, the packed weights).  The caches are keyed by
+        (data_ptr, _version) of every parameter, which in-place edits through ``.data`` (a manual EMA,
+        ``p.data.copy_()``) do not change: call this after such an edit.  Also used when the buffers a captured
+        graph points into go away (peer slabs re-allocated)."""
+        self._plans.clear()
+        if not graphs_only:
+            self._weights, self._weights_key = None, None
+
     def adopt_weights(self, module, packed: PackedWeights) -> None:
         """Use an already packed weight set (pips_b200/pack.py) for ``module``'s current parameters."""
         self._plans.clear()

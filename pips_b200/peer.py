@@ -34,8 +34,12 @@ class _DevPtr:
 
 
 class PeerSlab:
+    _generation = 0          # distinguishes slabs that happen to get the same device address from cudaMalloc
+
     def __init__(self, nbytes: int, rank: int, world: int, group, device: torch.device):
         lib = L.load()
+        PeerSlab._generation += 1
+        self.generation = PeerSlab._generation
         if world > L.MAX_PEERS:
             raise L.PipsCudaError(f"pips_b200: peer slabs support up to {L.MAX_PEERS} ranks per node")
         self.rank, self.world, self.group, self.device = rank, world, group, device
@@ -117,7 +121,7 @@ class PeerPlan:
         self.off_vis = self.off_coords + iters * B * S * self.n_total * 2
         self.off_ffeat = self.off_vis + B * S * self.n_total
         self.words = self.off_ffeat + B * self.n_total * LATENT
-        self.key = (slab.local, iters, B, S, per)
+        self.key = (slab.generation, slab.local, tuple(slab.ptrs), iters, B, S, per)
 
     @staticmethod
     def words_needed(world: int, iters: int, B: int, S: int, per: int) -> int:

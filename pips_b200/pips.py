@@ -131,11 +131,14 @@ class Pips(nn.Module):
         return self
 
     # ------------------------------------------------------------------ forward
-    def encode(self, rgbs: torch.Tensor) -> torch.Tensor:
-        """nets/pips.py:436-445: normalise to [-1,1], fnet per frame -> (B,S,128,H8,W8) fp32."""
+    def encode(self, rgbs: torch.Tensor, torch_only: bool = False) -> torch.Tensor:
+        """nets/pips.py:436-445: normalise to [-1,1], fnet per frame -> (B,S,128,H8,W8) fp32.
+        ``torch_only``: the plain torch module with strict-fp32 cuDNN math -- what the supervised / training path
+        (torch_path.forward_torch) uses: it may run on nn.DataParallel replicas from worker threads (train.py:254),
+        where per-parameter-pointer graph caches would be re-captured on every call and stream capture is unsafe."""
         B, S, C, H, W = rgbs.shape
         # the split paths detach the weights: inference only (the training path keeps plain cuDNN + autograd)
-        infer = rgbs.is_cuda and not torch.is_grad_enabled()
+        infer = rgbs.is_cuda and not torch.is_grad_enabled() and not torch_only
         H8, W8 = H // self.stride, W // self.stride
         if self.fnet_mode == "tc" and infer:
             from .encoder_fast import fnet_tc, fnet_tc_graphed

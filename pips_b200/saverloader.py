@@ -14,6 +14,7 @@ and returns the step.  Additions:
 from __future__ import annotations
 
 import os
+import struct
 import pathlib
 import re
 
@@ -93,7 +94,7 @@ def _bind_pack(model, pack_path, write_pack):
                 print("...bound weight pack %s" % pack_path)
                 return
             print("...weight pack %s was made from other parameters; re-packing" % pack_path)
-        except (ValueError, KeyError, OSError) as e:
+        except (ValueError, KeyError, OSError, RuntimeError, struct.error) as e:   # PipsCudaError is a RuntimeError
             print("...weight pack %s is unreadable (%s); re-packing" % (pack_path, e))
     if write_pack:
         try:

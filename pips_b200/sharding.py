@@ -96,6 +96,7 @@ def refine_sharded_p2p(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_in
             grown = 2 * slab.nbytes                                         # amortise slowly growing particle counts
             slab.close()
         model._peer_slab = None
+        model.engine.invalidate(graphs_only=True)   # captured update kernels store through the old slab's peer mappings
         try:
             model._peer_slab = slab = PeerSlab(max(need, grown, 1 << 16), rank, world, group, dev)
         except L.PipsCudaError as e:        # raised on every rank together (peer.py): all fall back to NCCL

@@ -89,7 +89,7 @@ def forward_torch(model, xys, rgbs, coords_init=None, feat_init=None, iters=3, t
     H8, W8 = H // stride, W // stride
     L, r = model.corr_levels, model.corr_radius
 
-    fmaps = model.encode(rgbs)
+    fmaps = model.encode(rgbs, torch_only=True)          # no CUDA graphs / custom kernels on this path (DataParallel-safe)
     if sw is not None and getattr(sw, "save_this", False) and hasattr(sw, "summ_feats"):
         sw.summ_feats("1_model/0_fmaps", fmaps.unbind(1))                       # nets/pips.py:447-448
 

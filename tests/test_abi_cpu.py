@@ -88,7 +88,7 @@ def test_peer_plan_layout():
     from pips_b200.peer import FLAG_WORDS, PeerPlan
 
     class FakeSlab:
-        world, rank, local = 4, 2, 0x7000000000
+        world, rank, local, generation = 4, 2, 0x7000000000, 1
         ptrs = [0x7000000000 + r * (1 << 30) for r in range(4)]
 
     plan = PeerPlan(FakeSlab(), iters=6, B=4, S=8, per=257)
@@ -101,6 +101,9 @@ def test_peer_plan_layout():
         for r in range(4):
             assert bases[it][r] == FakeSlab.ptrs[r] + 4 * FLAG_WORDS + it * step and bases[it][r] % 8 == 0
     assert bases[5][0] + step == FakeSlab.ptrs[0] + 4 * plan.off_vis
+    # a re-allocated slab (new generation) never shares a graph plan with the old one, even at the same address
+    FakeSlab.generation = 2
+    assert PeerPlan(FakeSlab(), iters=6, B=4, S=8, per=257).key != plan.key
 
 
 def test_no_particles_raises_like_the_reference():

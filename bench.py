@@ -245,6 +245,91 @@ def cpu_baseline_leg():
             "sample": f"B={bs} of {B}, N={ns} of {N_PER_GPU}, iters={ITERS}, {reps} forwards incl. fnet, reference algorithm (all-pairs volume + dense heat-map)"}
 
 
+def _stats(per_ms: list) -> dict:
+    return {"min": round(min(per_ms), 3), "median": round(statistics.median(per_ms), 3), "max": round(max(per_ms), 3),
+            "stdev": round(statistics.pstdev(per_ms), 3), "n": len(per_ms)}
+
+
+def time_config(model, dev, world, *, Bc, Hc, Wc, n_global, stride, steps=5, warm=3, seed=3):
+    """One more BASELINE configuration through the same public call: device-resident loop and pinned-host loop,
+    CUDA events per step, L2 flushed before each step, max over ranks.  ``model`` carries the stride / sharding."""
+    import torch.distributed as dist
+    from pips_b200 import synthetic
+    rgbs_h = synthetic.smooth_video(Bc, S, Hc, Wc, seed=seed).to(torch.bfloat16).pin_memory()
+    xys_h = synthetic.random_queries(Bc, n_global, Hc, Wc, seed=seed + 1).pin_memory()
+    rgbs, xys = rgbs_h.to(dev), xys_h.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def run(step):
+        per = []
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); step(); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        per = [a.elapsed_time(b) for a, b in evs]
+        t = torch.tensor([sum(per) / steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), per
+
+    def step_device():
+        with torch.no_grad():
+            return model(xys, rgbs, iters=ITERS)
+
+    def step_host():
+        with torch.no_grad():
+            out = model(xys_h.to(dev, non_blocking=True), rgbs_h.to(dev, non_blocking=True), iters=ITERS)
+            return out[0][-1].cpu(), out[2].cpu()
+
+    for _ in range(warm):
+        out = step_device()
+    finite = bool(torch.isfinite(out[0][-1]).all())
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms_dev, per_dev = run(step_device)
+    step_host()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms_e2e, per_e2e = run(step_host)
+    upd = Bc * S * n_global * ITERS
+    return {"workload": f"B={Bc}, S={S}, {Hc}x{Wc} bf16 video, global N={n_global}, iters={ITERS}, stride={stride}, {world} GPU(s)",
+            "value": upd / (ms_dev * 1e-3), "unit": UNIT, "ms_per_step": ms_dev, "steps": steps, "finite": finite,
+            "e2e": {"value": upd / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": rgbs_h.numel() * rgbs_h.element_size() + xys_h.numel() * 4,
+                    "d2h_bytes_per_step": (Bc * S * n_global * 3) * 4},
+            "ms_per_step_stats_rank0": _stats(per_dev)}
+
+
+def chain_block(dev, precision, feat):
+    """BASELINE cfg 5: chained tracking over a 100-frame 360x640 clip, N=512, 8-frame windows, stride 4, one GPU
+    (chain_demo.py:40-83 semantics; all particles advance together, pips_b200/chain.py)."""
+    from pips_b200 import synthetic
+    from pips_b200.chain import track_chain
+    T, Hc, Wc, Nc = 100, 360, 640, 512
+    rgbs = synthetic.smooth_video(1, T, Hc, Wc, seed=99).to(dev)
+    xy0 = synthetic.random_queries(1, Nc, Hc, Wc, seed=98).to(dev)
+    model = synthetic.seeded_model(stride=4, precision=precision, feat_dtype=feat).to(dev).eval()
+    out = {"workload": f"{T}x{Hc}x{Wc} clip, N={Nc}, 8-frame windows, iters={ITERS}, stride 4, 1 GPU", "unit": "tracked particle-frames/s"}
+    for key, adv in (("visibility_driven", None), ("fixed_advance_7", 7)):
+        for _ in range(2):
+            track_chain(model, rgbs, xy0, iters=ITERS, advance=adv)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        trajs, rounds = track_chain(model, rgbs, xy0, iters=ITERS, return_rounds=True, advance=adv)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        # every round refines 8 frames of each still-active track; the fixed schedule makes that count data-independent
+        out[key] = {"rounds": rounds, "ms": ms, "value": T * Nc / (ms * 1e-3), "finite": bool(torch.isfinite(trajs).all()),
+                    "includes": "fnet of all 100 frames once + pyramid + every round's 6 iterations"}
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from pips_b200 import synthetic
@@ -275,6 +360,7 @@ def run_ours(args, rank, world, local_rank):
             return out[0][-1].cpu(), out[2].cpu()
 
     def timed(step, k):
+        """k steps, L2 flushed before each; returns (total seconds, [ms per step]) from CUDA events on this stream."""
         evs = []
         for _ in range(k):
             flush.zero_()
@@ -282,14 +368,15 @@ def run_ours(args, rank, world, local_rank):
             e0.record(); step(); e1.record()
             evs.append((e0, e1))
         torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in evs) / 1e3
+        per = [a.elapsed_time(b) for a, b in evs]
+        return sum(per) / 1e3, per
 
     for _ in range(max(3, args.warmup)):
         step_device()
     barrier()
     sampler = ClockSampler(dev)                      # every rank watches its own GPU
     sampler.start()
-    t_dev = timed(step_device, args.steps)
+    t_dev, per_dev = timed(step_device, args.steps)
     barrier()
     clocks = sampler.stop()
     if world > 1:
@@ -302,12 +389,40 @@ def run_ours(args, rank, world, local_rank):
     launches = (model.engine.launches + (encoder_fast.LAUNCHES[0] if model.fnet_mode == 'tc' else 0)) * args.steps
     step_host()
     barrier()
-    t_e2e = timed(step_host, args.steps)
+    t_e2e, per_e2e = timed(step_host, args.steps)
     barrier()
     if world > 1:
         t = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = t.tolist()
+
+    # ---- the other BASELINE configurations, through the same call (every rank takes part in the sharded ones)
+    extra = {}
+    if not args.no_extra:
+        def guarded(name, fn):
+            try:
+                extra[name] = fn()
+            except Exception as e:                      # noqa: BLE001 -- a failed extra block must not lose the main line
+                extra[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+        def fresh(stride):
+            m = synthetic.seeded_model(stride=stride, seed=0, head_scale=0.05, precision=args.precision, feat_dtype=args.feat).to(dev).eval()
+            if world > 1:
+                m.shard_particles()
+            return m
+
+        if world == 1:
+            if N_PER_GPU != 4096:
+                # the north-star target configuration: S=8, 384x512, N=4096, iters=6 on ONE B200 (>= 1 M updates/s asked)
+                guarded("n4096_1gpu", lambda: time_config(model, dev, 1, Bc=B, Hc=H, Wc=W, n_global=4096, stride=STRIDE, seed=1234))
+            guarded("cfg1_demo_shape_1gpu", lambda: time_config(fresh(4), dev, 1, Bc=1, Hc=360, Wc=640, n_global=256, stride=4, steps=10))
+            guarded("cfg4_1gpu", lambda: time_config(fresh(8), dev, 1, Bc=1, Hc=720, Wc=1280, n_global=16384, stride=8))
+            guarded("cfg5_chain_1gpu", lambda: chain_block(dev, args.precision, args.feat))
+        else:
+            # BASELINE cfg 3 as stated: FIXED N=4096 sharded over the ranks (strong scaling; the main line is weak scaling)
+            guarded("strong_cfg3", lambda: time_config(model, dev, world, Bc=B, Hc=H, Wc=W, n_global=4096, stride=STRIDE, seed=1234))
+            # BASELINE cfg 4: 8 x 720 x 1280, N=16384, B=1, particle-sharded (frames of the encoder sharded as well)
+            guarded("cfg4_sharded", lambda: time_config(fresh(8), dev, world, Bc=1, Hc=720, Wc=1280, n_global=16384, stride=8))
     if rank != 0:
         return
 
@@ -338,15 +453,22 @@ def run_ours(args, rank, world, local_rank):
     roofline_corr = {"kernel": "corr_gather_kernel", "bound": "hbm", "achieved": corr_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": corr_gbs / pk["hbm_gbs"], "traffic": None, "bytes_per_unit": unit_bytes,
                      "peak_source": pk["source"] + " (copy bandwidth)", "note": "pyramid is L2-resident at this config"}
+    # DRAM bytes per launch come from an `ncu --set full` capture (tools/ncu_traffic.py writes the file together with the
+    # digest of the kernel sources it profiled); they are reported only when that digest is the library's that runs now.
     try:
+        from pips_b200 import _build
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             tr = json.load(f)
-        roofline["traffic"] = tr.get("gemm_tc_bytes_per_launch")
-        roofline_corr["traffic"] = tr.get("corr_gather_bytes_per_launch")
+        if tr.get("source_digest") == _build.source_digest():
+            roofline["traffic"] = tr.get("gemm_fc_bytes_per_launch")
+            roofline_corr["traffic"] = tr.get("corr_gather_bytes_per_launch")
+            roofline["traffic_source"] = roofline_corr["traffic_source"] = tr.get("source")
+        else:
+            roofline["traffic_source"] = roofline_corr["traffic_source"] = "profiles/ncu_traffic.json is from other kernel sources: not reported"
     except Exception:
         pass
     eager = None
-    if world == 1 and args.with_eager:
+    if world == 1 and not args.no_eager:
         # the reference's algorithm as eager torch ops on THIS GPU (all-pairs volume, dense heat-map, strict-fp32
         # cuDNN/cuBLAS) -- pips_b200/torch_path.py, which is pinned to the reference's outputs on CPU.  Context only.
         from pips_b200.torch_path import forward_torch
@@ -381,6 +503,8 @@ def run_ours(args, rank, world, local_rank):
             "kernel_ms_per_iteration": {k: round(v, 4) for k, v in per_iter.items()},
             "loop_only": {"ms_per_iteration": sum(per_iter.values()), "updates_per_s": B * S * N_PER_GPU / (sum(per_iter.values()) * 1e-3)},
             "whole_path_tensor_frac": (updates * UNIT_FLOP / (t_dev / args.steps)) / 1e12 / pk["bf16_tflops_sustained"] / world}
+    line["ms_per_step_stats_rank0"] = {"device_loop": _stats(per_dev), "e2e_loop": _stats(per_e2e)}
+    line.update(extra)
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if eager is not None:
@@ -413,7 +537,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("PIPS_B200_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--feat", default=os.environ.get("PIPS_B200_FEAT", "fp32"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--with-eager", action="store_true", help="also time the eager-torch restatement of the reference on this GPU")
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager-torch restatement of the reference on this GPU")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configurations (n4096_1gpu, cfg1/4/5, strong_cfg3, cfg4_sharded)")
     ap.add_argument("--particles", type=int, default=0, help="particles per GPU (default 1024 = BASELINE cfg2; 4096 = cfg3 on one GPU)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

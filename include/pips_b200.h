@@ -164,7 +164,9 @@ int pips_resize_split3(const float* src, int N, int Hs, int Ws, int C, float* ds
                        void* stream);
 
 /* bf16 (hi, lo) flavours of the two functions above: the operand layout of pips_conv_tc (row stride pair_ld /
- * Ctot channels; channels beyond C are left untouched and must be zero). */
+ * Ctot channels).  The K-padding channels are written as zero by these calls themselves: pips_inorm_apply_pair
+ * zeroes [C, pair_ld); pips_resize_pair zeroes [c_off+C, Ctot) when fewer than 64 channels remain after its slice
+ * (i.e. the slice is the last one before the padding of a row padded to a multiple of 64). */
 int pips_inorm_apply_pair(const float* y, const float* stats_y, const float* r, const float* stats_r, int relu_main, int relu_out,
                           float* out_plain, void* out_hi, void* out_lo, int pair_ld, int N, int HW, int C, void* stream);
 int pips_resize_pair(const float* src, int N, int Hs, int Ws, int C, void* dst_hi, void* dst_lo, int Ho, int Wo, int Ctot, int c_off,

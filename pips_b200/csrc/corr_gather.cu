@@ -7,13 +7,17 @@
 // dot products with the 8x8 pixel footprint those taps share (they have one common fractional
 // offset).  Zero padding outside the map (grid_sample's default) is exactly the TMA out-of-bounds fill.
 //
-// Work unit = one (b, s, n): for each of the 4 pyramid levels two TMA boxes {128 ch, 8 px, 4 rows}
+// Work unit = one (b, s, n): for each of the 4 pyramid levels four TMA boxes {128 ch, 8 px, 2 rows}
 // are staged into shared memory (channels-last pyramid => every pixel is one contiguous 512 B / 256 B
-// line), each lane owns 4 channels, the 32 partial dot products of a box are reduced with a 31-shuffle
-// butterfly that leaves pixel i's total in lane i, and the 7x7 blend, the sin/cos embedding and the
+// line), each lane owns 4 channels, the 16 partial dot products of a box are reduced with a 16-shuffle
+// butterfly that leaves pixel i's total in lanes 2i, 2i+1, and the 7x7 blend, the sin/cos embedding and the
 // feature copy are assembled in a per-warp row buffer that is written out as one contiguous mixer row.
 // Every warp runs its own 3-deep TMA ring (it is both producer and consumer, so only "full" mbarriers
-// are needed); 4 warps per CTA, persistent grid.
+// are needed); 8 warps per CTA, persistent grid.
+//
+// Round 2: the round-1 kernel used 4-row boxes (16 KB in fp32), i.e. 50 KB of smem per warp and 4 warps per SM --
+// ncu showed it latency-bound (6 % of the warp slots active, issue 26 %, L2 35 %), not bandwidth-bound.  Two-row
+// boxes halve the ring (27 KB per warp) and give 8 warps per SM with the same number of bytes in flight per SM.
 //
 // Algorithmic bytes per unit: 4 levels x 64 px x 128 ch x e_f  +  128 x 4 (query)
 // +  output row.
@@ -22,16 +26,23 @@
 
 namespace pips {
 
-constexpr int CG_WARPS = 4;
+constexpr int CG_WARPS = 8;
 constexpr int CG_STAGES = 3;
-constexpr int CG_ROWS_PER_BOX = 4;
+constexpr int CG_ROWS_PER_BOX = 2;
 constexpr int CG_ROWBUF = PIPS_KITCHEN_PAD;   // 576 floats
+constexpr uint32_t CG_AUX_BYTES = CG_ROWBUF * 4 + 64 * 4 + 128;    // per warp: row buffer, 64 dot products, 3 mbarriers
 
 template <typename T>
 struct CgCfg {
-    static constexpr uint32_t kBoxBytes = CG_ROWS_PER_BOX * 8 * 128 * sizeof(T);
-    static constexpr uint32_t kWarpBytes = CG_STAGES * kBoxBytes + CG_ROWBUF * 4 + 64 * 4 + 128 /*barriers; keeps 128 B alignment*/;
-    static constexpr uint32_t kSmemBytes = CG_WARPS * kWarpBytes + 128;
+    static constexpr uint32_t kPixBytes = 128 * sizeof(T);                      // one pixel = 128 channels
+    static constexpr uint32_t kBoxBytes = CG_ROWS_PER_BOX * 8 * kPixBytes;      // 8 KB (fp32) / 4 KB (bf16)
+    // [warp][stage] boxes first, each aligned to its own size (the pixel order inside a box is XOR-permuted per lane,
+    // which needs the box base to have zero bits where the pixel index goes), then the per-warp auxiliary blocks
+    static constexpr uint32_t kSmemBytes = CG_WARPS * CG_STAGES * kBoxBytes + CG_WARPS * CG_AUX_BYTES + kBoxBytes;
+};
+
+struct CgMaps {
+    CUtensorMap m[PIPS_LEVELS];
 };
 
 struct CgArgs {
@@ -61,54 +72,55 @@ __device__ __forceinline__ float4 ld_chan4(const __nv_bfloat16* p) {
 
 struct UnitInfo {
     float cx, cy;      // coords of (b,s,n), level-0 pixels
-    int frame;         // b*S + s
+    int frame;         // pyramid frame index
+    int b, n, s;
     int valid;
+    int ox, oy;        // lane l < 4: TMA box origin (first column, first row) of pyramid level l for this unit
 };
 
-__device__ __forceinline__ UnitInfo load_unit(const CgArgs& a, long long u, long long total) {
+// Unit u = (seq, s) with seq = b*N + n (the mixer's row order); S == 8.  Besides the unit's coordinates every lane
+// computes the box origin of ONE pyramid level (lane & 3), so that issuing a TMA box later costs two shuffles instead
+// of a clamp / floor / convert chain executed by lane 0 alone while 31 lanes wait.  Coordinates are clamped in float
+// so that diverged or non-finite tracks cannot overflow the int conversion (beyond +-8 px of the map all taps are zero).
+__device__ __forceinline__ UnitInfo load_unit(const CgArgs& a, int u, int total) {
     UnitInfo ui;
     ui.valid = u < total;
-    ui.cx = 0.f; ui.cy = 0.f; ui.frame = 0;
+    ui.cx = 0.f; ui.cy = 0.f; ui.frame = 0; ui.b = 0; ui.n = 0; ui.s = 0; ui.ox = 0; ui.oy = 0;
     if (ui.valid) {
-        const int s = static_cast<int>(u % a.S);
-        const long long seq = u / a.S;
-        const int b = static_cast<int>(seq / a.N), n = static_cast<int>(seq % a.N);
-        const float2 c = *reinterpret_cast<const float2*>(a.coords + ((static_cast<size_t>(b) * a.S + s) * a.N + n) * 2);
+        ui.s = u & 7;
+        const int seq = u >> 3;
+        ui.b = seq / a.N; ui.n = seq - ui.b * a.N;
+        const float2 c = *reinterpret_cast<const float2*>(a.coords + ((static_cast<size_t>(ui.b) * 8 + ui.s) * a.N + ui.n) * 2);
         ui.cx = c.x; ui.cy = c.y;
         // chained windows replicate the clip's last frame past its end (chain_demo.py:50-52)
-        ui.frame = a.frame_base ? b * a.T + min(a.frame_base[seq] + s, a.T - 1) : b * a.S + s;
+        ui.frame = a.frame_base ? ui.b * a.T + min(a.frame_base[seq] + ui.s, a.T - 1) : ui.b * 8 + ui.s;
+        const int level = threadIdx.x & 3;
+        const float sc = 1.0f / static_cast<float>(1 << level);        // coords / 2**i  (nets/pips.py:373), exact
+        const float cxl = fminf(fmaxf(c.x * sc, -8.0f), static_cast<float>(a.W[level]) + 8.0f);
+        const float cyl = fminf(fmaxf(c.y * sc, -8.0f), static_cast<float>(a.H[level]) + 8.0f);
+        ui.ox = static_cast<int>(floorf(cxl)) - PIPS_RADIUS;
+        ui.oy = static_cast<int>(floorf(cyl)) - PIPS_RADIUS;
     }
     return ui;
 }
 
-// TMA box origin of (level, half) for a unit; coordinates are clamped in float so that diverged or
-// non-finite tracks cannot overflow the int conversion (anything beyond +-8 px of the map is all-zero anyway).
-__device__ __forceinline__ void box_origin(const CgArgs& a, const UnitInfo& ui, int level, int half, int& x0, int& y0) {
-    const float sc = 1.0f / static_cast<float>(1 << level);        // coords / 2**i  (nets/pips.py:373), exact
-    const float cxl = fminf(fmaxf(ui.cx * sc, -8.0f), static_cast<float>(a.W[level]) + 8.0f);
-    const float cyl = fminf(fmaxf(ui.cy * sc, -8.0f), static_cast<float>(a.H[level]) + 8.0f);
-    x0 = static_cast<int>(floorf(cxl)) - PIPS_RADIUS;
-    y0 = static_cast<int>(floorf(cyl)) - PIPS_RADIUS + half * CG_ROWS_PER_BOX;
-}
-
 template <typename T>
 __global__ void __launch_bounds__(CG_WARPS * 32)
-corr_gather_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1,
-                   const __grid_constant__ CUtensorMap map2, const __grid_constant__ CUtensorMap map3, const CgArgs a) {
+corr_gather_kernel(const __grid_constant__ CgMaps maps, const CgArgs a) {
     using Cfg = CgCfg<T>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + Cfg::kBoxBytes - 1) &
+                                               ~static_cast<uintptr_t>(Cfg::kBoxBytes - 1));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t* wbase = smem + warp * Cfg::kWarpBytes;
-    T* stage_buf = reinterpret_cast<T*>(wbase);
-    float* rowbuf = reinterpret_cast<float*>(wbase + CG_STAGES * Cfg::kBoxBytes);
+    uint8_t* stage_buf = smem + static_cast<size_t>(warp) * CG_STAGES * Cfg::kBoxBytes;
+    float* rowbuf = reinterpret_cast<float*>(smem + CG_WARPS * CG_STAGES * Cfg::kBoxBytes + warp * CG_AUX_BYTES);
     float* dots = rowbuf + CG_ROWBUF;
     const uint32_t bar0 = smem_u32(dots + 64);
     const uint32_t stage0 = smem_u32(stage_buf);
 
-    const long long total = static_cast<long long>(a.B) * a.S * a.N;
-    const long long nwarps = static_cast<long long>(gridDim.x) * CG_WARPS;
-    long long u = static_cast<long long>(blockIdx.x) * CG_WARPS + warp;
+    const int total = a.B * 8 * a.N;
+    const int nwarps = static_cast<int>(gridDim.x) * CG_WARPS;
+    int u = static_cast<int>(blockIdx.x) * CG_WARPS + warp;
     if (u >= total) return;                         // whole warp exits together
 
     if (lane == 0) {
@@ -118,23 +130,27 @@ corr_gather_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     for (int i = PIPS_KITCHEN + lane; i < CG_ROWBUF; i += 32) rowbuf[i] = 0.f;     // zero K padding, written once
     __syncwarp();
 
-    const CUtensorMap* maps[PIPS_LEVELS] = {&map0, &map1, &map2, &map3};
-    auto issue = [&](const UnitInfo& ui, int j, int slot) {
-        // j in [0,8): level = j>>1, half = j&1
+    // Lane l accumulates pixel (i ^ (l >> 1)) of a box in acc[i]: with that order every butterfly step is
+    // "keep the low half, send the high half" for ALL lanes -- no per-lane selects (2 FSEL per exchanged value before).
+    const uint32_t pix_xor = static_cast<uint32_t>(lane >> 1) * Cfg::kPixBytes;
+    const uint32_t lane_off = static_cast<uint32_t>(lane) * 4 * sizeof(T);
+
+    // box j of a unit: level = j >> 2, rows 2 (j & 3), 2 (j & 3) + 1 of the level's 8x8 footprint
+    auto issue = [&](const UnitInfo& ui, int level, int part, int slot) {
+        const int x0 = __shfl_sync(0xffffffffu, ui.ox, level);
+        const int y0 = __shfl_sync(0xffffffffu, ui.oy, level) + part * CG_ROWS_PER_BOX;
         if (lane == 0) {
-            int x0, y0;
-            box_origin(a, ui, j >> 1, j & 1, x0, y0);
             const uint32_t bar = bar0 + 8 * slot;
             mbar_arrive_expect_tx(bar, Cfg::kBoxBytes);
-            tma_load_4d(stage0 + slot * Cfg::kBoxBytes, maps[j >> 1], bar, 0, x0, y0, ui.frame);
+            tma_load_4d(stage0 + slot * Cfg::kBoxBytes, &maps.m[level], bar, 0, x0, y0, ui.frame);
         }
     };
 
     UnitInfo cur = load_unit(a, u, total);
     UnitInfo nxt = load_unit(a, u + nwarps, total);
     float4 q = *reinterpret_cast<const float4*>(a.ffeats + static_cast<size_t>(u) * 128 + lane * 4);
-    issue(cur, 0, 0);
-    issue(cur, 1, 1);
+    issue(cur, 0, 0, 0);
+    issue(cur, 0, 1, 1);
     int slot = 0;
     uint32_t parity = 0;
 
@@ -145,57 +161,40 @@ corr_gather_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
         const UnitInfo nxt2 = load_unit(a, u + 2 * nwarps, total);
 
 #pragma unroll 1
-        for (int j = 0; j < 8; ++j) {
-            // keep the ring full: item j+2 of this unit, or item j-6 of the next one
-            {
-                int slot2 = slot + 2;
-                if (slot2 >= CG_STAGES) slot2 -= CG_STAGES;
-                if (j < 6) issue(cur, j + 2, slot2);
-                else if (nxt.valid) issue(nxt, j - 6, slot2);
-            }
-            mbar_wait(bar0 + 8 * slot, parity);
-            const T* sb = stage_buf + static_cast<size_t>(slot) * (Cfg::kBoxBytes / sizeof(T)) + lane * 4;
-            float acc[32];
+        for (int level = 0; level < PIPS_LEVELS; ++level) {
 #pragma unroll
-            for (int p = 0; p < 32; ++p) {
-                const float4 v = ld_chan4(sb + p * 128);
-                acc[p] = (q.x * v.x + q.y * v.y) + (q.z * v.z + q.w * v.w);
-            }
-            // butterfly: after the 5 steps lane i holds the full dot product of pixel i of this box
+            for (int part = 0; part < 4; ++part) {
+                // keep the ring full: the box two ahead (same level, next level, or the next unit's first two)
+                {
+                    int slot2 = slot + 2;
+                    if (slot2 >= CG_STAGES) slot2 -= CG_STAGES;
+                    if (part < 2) issue(cur, level, part + 2, slot2);
+                    else if (level < PIPS_LEVELS - 1) issue(cur, level + 1, part - 2, slot2);
+                    else if (nxt.valid) issue(nxt, 0, part - 2, slot2);
+                }
+                mbar_wait(bar0 + 8 * slot, parity);
+                const uint8_t* sb = stage_buf + static_cast<size_t>(slot) * Cfg::kBoxBytes + lane_off;
+                float acc[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const bool up = lane & 16;
-                const float send = up ? acc[i] : acc[i + 16], keep = up ? acc[i + 16] : acc[i];
-                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
+                for (int i = 0; i < 16; ++i) {
+                    const float4 v = ld_chan4(reinterpret_cast<const T*>(sb + ((static_cast<uint32_t>(i) * Cfg::kPixBytes) ^ pix_xor)));
+                    acc[i] = fmaf(q.w, v.w, fmaf(q.z, v.z, fmaf(q.y, v.y, q.x * v.x)));
+                }
+                // butterfly: after the 5 steps lanes 2p and 2p+1 hold the full dot product of pixel p of this box
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const bool up = lane & 8;
-                const float send = up ? acc[i] : acc[i + 8], keep = up ? acc[i + 8] : acc[i];
-                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
+                for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i + 8], 16);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const bool up = lane & 4;
-                const float send = up ? acc[i] : acc[i + 4], keep = up ? acc[i + 4] : acc[i];
-                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
+                for (int i = 0; i < 4; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i + 4], 8);
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const bool up = lane & 2;
-                const float send = up ? acc[i] : acc[i + 2], keep = up ? acc[i + 2] : acc[i];
-                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                for (int i = 0; i < 2; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i + 2], 4);
+                acc[0] += __shfl_xor_sync(0xffffffffu, acc[1], 2);
+                acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+                // corrs / sqrt(C)  (nets/pips.py:397); dots[by * 8 + ax], by = 2 part + box row, ax = pixel in the row
+                if (!(lane & 1)) dots[part * 16 + (lane >> 1)] = __fdiv_rn(acc[0], 11.313708498984761f);
+                __syncwarp();                           // stage slot fully consumed, dots visible
+                if (++slot == CG_STAGES) { slot = 0; parity ^= 1; }
             }
             {
-                const bool up = lane & 1;
-                const float send = up ? acc[0] : acc[1], keep = up ? acc[1] : acc[0];
-                acc[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-            }
-            // corrs / sqrt(C)  (nets/pips.py:397)
-            dots[(j & 1) * 32 + lane] = __fdiv_rn(acc[0], 11.313708498984761f);
-            __syncwarp();                           // stage slot fully consumed, dots visible
-            if (j & 1) {
-                const int level = j >> 1;
                 const float sc = 1.0f / static_cast<float>(1 << level);
                 const float cxl = fminf(fmaxf(cur.cx * sc, -8.0f), static_cast<float>(a.W[level]) + 8.0f);
                 const float cyl = fminf(fmaxf(cur.cy * sc, -8.0f), static_cast<float>(a.H[level]) + 8.0f);
@@ -209,16 +208,12 @@ corr_gather_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
                 }
                 __syncwarp();                       // dots are rewritten by the next level
             }
-            if (++slot == CG_STAGES) { slot = 0; parity ^= 1; }
         }
 
         // feature copy + motion embedding (utils/misc.py:44-69; flows nets/pips.py:518-520)
         {
-            const int s = static_cast<int>(u % a.S);
-            const long long seq = u / a.S;
-            const int b = static_cast<int>(seq / a.N), n = static_cast<int>(seq % a.N);
-            const float2 c0 = *reinterpret_cast<const float2*>(a.coords + ((static_cast<size_t>(b) * a.S + 0) * a.N + n) * 2);
-            const float flow_x = cur.cx - c0.x, flow_y = cur.cy - c0.y, t = a.times[s];
+            const float2 c0 = *reinterpret_cast<const float2*>(a.coords + (static_cast<size_t>(cur.b) * 8 * a.N + cur.n) * 2);
+            const float flow_x = cur.cx - c0.x, flow_y = cur.cy - c0.y, t = a.times[cur.s];
             *reinterpret_cast<float4*>(rowbuf + lane * 4) = q;
             const float div = static_cast<float>(lane) * 31.25f;          // arange(0,64,2) * (1000/64)
             float sn, cs;
@@ -237,11 +232,16 @@ corr_gather_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
                 const float4 v = *reinterpret_cast<const float4*>(rowbuf + g * 4);
                 if (a.x_f32) *reinterpret_cast<float4*>(a.x_f32 + ro + g * 4) = v;
                 if (a.x_hi) {
-                    __nv_bfloat16 h[4], l[4];
-                    split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]);
-                    split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
-                    *reinterpret_cast<uint2*>(a.x_hi + ro + g * 4) = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
-                    if (a.x_lo) *reinterpret_cast<uint2*>(a.x_lo + ro + g * 4) = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
+                    // v ~= hi + lo, both bf16 (same roundings as split_bf16, on packed pairs)
+                    const uint32_t h0 = cvt_bf16x2(v.x, v.y), h1 = cvt_bf16x2(v.z, v.w);
+                    *reinterpret_cast<uint2*>(a.x_hi + ro + g * 4) = make_uint2(h0, h1);
+                    if (a.x_lo) {
+                        const float2 l0 = fma2(make_float2(__uint_as_float(h0 << 16), __uint_as_float(h0 & 0xffff0000u)), bcast2(-1.0f),
+                                               make_float2(v.x, v.y));
+                        const float2 l1 = fma2(make_float2(__uint_as_float(h1 << 16), __uint_as_float(h1 & 0xffff0000u)), bcast2(-1.0f),
+                                               make_float2(v.z, v.w));
+                        *reinterpret_cast<uint2*>(a.x_lo + ro + g * 4) = make_uint2(cvt_bf16x2(l0.x, l0.y), cvt_bf16x2(l1.x, l1.y));
+                    }
                 }
             }
         }
@@ -254,7 +254,7 @@ corr_gather_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
 
 template <typename T>
 static int launch_corr_gather(const void* const* lvl, CUtensorMapDataType dt, const CgArgs& args, int frames, cudaStream_t st) {
-    CUtensorMap maps[PIPS_LEVELS];
+    CgMaps maps;
     for (int l = 0; l < PIPS_LEVELS; ++l) {
         const cuuint64_t es = sizeof(T);
         cuuint64_t gdim[4] = {128, static_cast<cuuint64_t>(args.W[l]), static_cast<cuuint64_t>(args.H[l]), static_cast<cuuint64_t>(frames)};
@@ -262,7 +262,7 @@ static int launch_corr_gather(const void* const* lvl, CUtensorMapDataType dt, co
                               static_cast<cuuint64_t>(args.H[l]) * args.W[l] * 128 * es};
         cuuint32_t box[4] = {128, 8, CG_ROWS_PER_BOX, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        if (!encode_tiled(&maps[l], dt, 4, const_cast<void*>(lvl[l]), gdim, gstr, box, estr, CU_TENSOR_MAP_SWIZZLE_NONE))
+        if (!encode_tiled(&maps.m[l], dt, 4, const_cast<void*>(lvl[l]), gdim, gstr, box, estr, CU_TENSOR_MAP_SWIZZLE_NONE))
             return fail("pips_corr_gather: cuTensorMapEncodeTiled failed");
     }
     using Cfg = CgCfg<T>;
@@ -272,11 +272,12 @@ static int launch_corr_gather(const void* const* lvl, CUtensorMapDataType dt, co
         if (e != cudaSuccess) return fail_cuda("pips_corr_gather: smem attribute", e);
     }
     const long long units = static_cast<long long>(args.B) * args.S * args.N;
-    const int ctas_per_sm = sizeof(T) == 2 ? 2 : 1;
+    if (units >= (1LL << 31)) return fail("pips_corr_gather: more than 2^31 units in one call");
+    const int ctas_per_sm = 1;                                // 8 warps x (3 x 8 KB + 2.6 KB) fill one SM's shared memory (fp32)
     long long grid = (units + CG_WARPS - 1) / CG_WARPS;
     const long long cap = static_cast<long long>(sm_count()) * ctas_per_sm;
     if (grid > cap) grid = cap;
-    corr_gather_kernel<T><<<static_cast<unsigned>(grid), CG_WARPS * 32, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], args);
+    corr_gather_kernel<T><<<static_cast<unsigned>(grid), CG_WARPS * 32, Cfg::kSmemBytes, st>>>(maps, args);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail_cuda("pips_corr_gather: launch", e);
 }

@@ -72,9 +72,19 @@ struct ApplyArgs {
 __global__ void __launch_bounds__(256)
 inorm_apply_kernel(const ApplyArgs a, size_t total4) {
     const int c4n = a.C >> 2;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int c4 = static_cast<int>(i % c4n);
-        const size_t pix = i / c4n;                      // n*HW + p
+    // with a bf16 pair output the loop also covers the pair's padding channels [C, pair_ld) and writes them as zero
+    // (they are K padding of the next convolution): no separate fill pass over the operand
+    const int c4p = a.out_hi ? a.pair_ld >> 2 : c4n;
+    for (size_t j = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; j < total4; j += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c4 = static_cast<int>(j % c4p);
+        const size_t pix = j / c4p;                      // n*HW + p
+        if (c4 >= c4n) {
+            const size_t o = pix * a.pair_ld + c4 * 4;
+            *reinterpret_cast<uint2*>(a.out_hi + o) = make_uint2(0u, 0u);
+            *reinterpret_cast<uint2*>(a.out_lo + o) = make_uint2(0u, 0u);
+            continue;
+        }
+        const size_t i = pix * c4n + c4;
         const int n = static_cast<int>(pix / a.HW);
         float4 v = reinterpret_cast<const float4*>(a.y)[i];
         if (a.stats_y) {
@@ -116,7 +126,10 @@ inorm_apply_kernel(const ApplyArgs a, size_t total4) {
 __global__ void __launch_bounds__(256)
 resize_split3_kernel(const float* __restrict__ src, int Hs, int Ws, int C, float* __restrict__ dst, __nv_bfloat16* __restrict__ dst_hi,
                      __nv_bfloat16* __restrict__ dst_lo, int Ho, int Wo, int Ctot, int c_off, size_t total4) {
-    const int c4n = C >> 2;
+    // bf16 pair output: when fewer than 64 channels remain after this slice they are the concat's K padding (rows are padded
+    // to a multiple of 64) -- this call writes them as zero, so the concat needs no fill pass
+    const int tail = (!dst && Ctot - (c_off + C) < 64) ? Ctot - (c_off + C) : 0;
+    const int c4n = (C + tail) >> 2, c4v = C >> 2;
     // at::native area_pixel_compute_scale(align_corners=true): (in - 1) / (out - 1), 0 when out == 1
     const float sh = Ho > 1 ? static_cast<float>(Hs - 1) / static_cast<float>(Ho - 1) : 0.f;
     const float sw = Wo > 1 ? static_cast<float>(Ws - 1) / static_cast<float>(Wo - 1) : 0.f;
@@ -126,13 +139,19 @@ resize_split3_kernel(const float* __restrict__ src, int Hs, int Ws, int C, float
         const int ox = static_cast<int>(p % Wo); p /= Wo;
         const int oy = static_cast<int>(p % Ho);
         const int n = static_cast<int>(p / Ho);
+        if (c4 >= c4v) {
+            const size_t o = ((static_cast<size_t>(n) * Ho + oy) * Wo + ox) * static_cast<size_t>(Ctot) + c_off + c4 * 4;
+            *reinterpret_cast<uint2*>(dst_hi + o) = make_uint2(0u, 0u);
+            *reinterpret_cast<uint2*>(dst_lo + o) = make_uint2(0u, 0u);
+            continue;
+        }
         const float fy = sh * oy, fx = sw * ox;
         const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
         const int yp = y0 < Hs - 1 ? 1 : 0, xp = x0 < Ws - 1 ? 1 : 0;
         const float ly = fy - y0, lx = fx - x0, hy = 1.f - ly, hx = 1.f - lx;
         const float4* b = reinterpret_cast<const float4*>(src + ((static_cast<size_t>(n) * Hs + y0) * Ws + x0) * C) + c4;
-        const float4 v00 = b[0], v01 = b[static_cast<size_t>(xp) * c4n];
-        const float4 v10 = b[static_cast<size_t>(yp) * Ws * c4n], v11 = b[(static_cast<size_t>(yp) * Ws + xp) * c4n];
+        const float4 v00 = b[0], v01 = b[static_cast<size_t>(xp) * c4v];
+        const float4 v10 = b[static_cast<size_t>(yp) * Ws * c4v], v11 = b[(static_cast<size_t>(yp) * Ws + xp) * c4v];
         float4 v;
         v.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x);
         v.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y);
@@ -228,7 +247,7 @@ static int inorm_apply_impl(const float* y, const float* stats_y, const float* r
     a.y = y; a.stats_y = stats_y; a.r = r; a.stats_r = stats_r; a.relu_main = relu_main; a.relu_out = relu_out;
     a.out_plain = out_plain; a.out_split = out_split; a.split_ld = split_ld; a.HW = HW; a.C = C;
     a.out_hi = static_cast<__nv_bfloat16*>(out_hi); a.out_lo = static_cast<__nv_bfloat16*>(out_lo); a.pair_ld = pair_ld;
-    const size_t total4 = static_cast<size_t>(N) * HW * (C / 4);
+    const size_t total4 = static_cast<size_t>(N) * HW * ((out_hi ? pair_ld : C) / 4);
     inorm_apply_kernel<<<grid_for(total4), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, total4);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail_cuda("pips_inorm_apply", e);
@@ -252,7 +271,8 @@ static int resize_impl(const float* src, int N, int Hs, int Ws, int C, float* ds
     if (!src || (!dst && (!dst_hi || !dst_lo))) return fail("pips_resize: null pointer");
     if (N <= 0 || Hs <= 0 || Ws <= 0 || Ho <= 0 || Wo <= 0 || (C % 4) || (Ctot % 4) || (c_off % 4) || c_off + C > Ctot)
         return fail("pips_resize: bad shape");
-    const size_t total4 = static_cast<size_t>(N) * Ho * Wo * (C / 4);
+    const int tail = (!dst && Ctot - (c_off + C) < 64) ? Ctot - (c_off + C) : 0;
+    const size_t total4 = static_cast<size_t>(N) * Ho * Wo * ((C + tail) / 4);
     resize_split3_kernel<<<grid_for(total4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         src, Hs, Ws, C, dst, static_cast<__nv_bfloat16*>(dst_hi), static_cast<__nv_bfloat16*>(dst_lo), Ho, Wo, Ctot, c_off, total4);
     cudaError_t e = cudaGetLastError();

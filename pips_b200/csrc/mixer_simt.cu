@@ -302,14 +302,13 @@ extern "C" int pips_tokenmix(float* x, int seqs, const float* ln1_w, const float
     if (seqs <= 0) return fail("pips_tokenmix: no sequences");
     if (!y_hi && !y_f32) return fail("pips_tokenmix: no output buffer");
     {
-        // PIPS_B200_TOKENMIX=tc selects the tensor-core variant (tokenmix_tc.cu).  It is correct (tests) and halves
-        // the instruction count, but in its current one-sequence-at-a-time form it is latency-bound on the two
-        // MMA -> mbarrier round trips per track (2 CTAs/SM): 0.147 ms vs 0.117 ms per launch at 4096 tracks, so the
-        // CUDA-core kernel below stays the default until the tc kernel is software-pipelined across tracks.
+        // bf16 / bf16x3 precisions run the tensor-core kernel (tokenmix_tc.cu: both contractions as tcgen05 MMAs, software-
+        // pipelined over the four channel tiles, 4 CTAs per SM); PIPS_B200_TOKENMIX=simt keeps the CUDA-core kernel below,
+        // which is also the fp32-precision path.
         static int use_tc = -1;
         if (use_tc < 0) {
             const char* e = getenv("PIPS_B200_TOKENMIX");
-            use_tc = (e && e[0] == 't') ? 1 : 0;
+            use_tc = (e && e[0] == 's') ? 0 : 1;
         }
         if (use_tc && y_hi && !y_f32)
             return tokenmix_tc_launch(x, seqs, ln1_w, ln1_b, w1, b1, w2, b2, ln2_w, ln2_b, y_hi, y_lo, static_cast<cudaStream_t>(stream));

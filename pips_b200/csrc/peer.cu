@@ -25,6 +25,21 @@ __global__ void __launch_bounds__(256) peer_scatter_kernel(const float* __restri
     }
 }
 
+// 16-byte form (cols, cols_total, col_offset multiples of 4, pointers 16-byte aligned): a warp stores 512 contiguous
+// bytes per peer and instruction -- NVLink carries writes in packets of up to 256 B of payload behind one header, so
+// whole lines matter far more here than for local stores.
+__global__ void __launch_bounds__(256) peer_scatter4_kernel(const float4* __restrict__ src, int rows, int cols4,
+                                                            pips_peer_out dst, int cols_total4, int col_offset4) {
+    const size_t total = static_cast<size_t>(rows) * cols4;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t r = i / cols4, c = i - r * cols4;
+        const float4 v = src[i];
+        const size_t o = r * cols_total4 + col_offset4 + c;
+        for (int p = 0; p < dst.n_peers; ++p) reinterpret_cast<float4*>(dst.out[p])[o] = v;
+    }
+}
+
 struct FlagPtrs {
     int* f[PIPS_MAX_PEERS];
 };
@@ -121,11 +136,17 @@ extern "C" int pips_peer_scatter(const float* src, int rows, int cols, float* co
         if (!dst[r]) return fail("pips_peer_scatter: null destination");
         d.out[r] = dst[r];
     }
-    const size_t total = static_cast<size_t>(rows) * cols;
+    bool vec = (cols % 4 == 0) && (cols_total % 4 == 0) && (col_offset % 4 == 0) && !(reinterpret_cast<uintptr_t>(src) & 15);
+    for (int r = 0; r < n_peers; ++r) vec = vec && !(reinterpret_cast<uintptr_t>(dst[r]) & 15);
+    const size_t total = static_cast<size_t>(rows) * cols / (vec ? 4 : 1);
     const size_t blocks = (total + 255) / 256;
     const size_t cap = static_cast<size_t>(sm_count()) * 8;
-    peer_scatter_kernel<<<static_cast<unsigned>(blocks < cap ? blocks : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        src, rows, cols, d, cols_total, col_offset);
+    const unsigned grid = static_cast<unsigned>(blocks < cap ? blocks : cap);
+    if (vec)
+        peer_scatter4_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(src), rows, cols / 4, d,
+                                                                                 cols_total / 4, col_offset / 4);
+    else
+        peer_scatter_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, rows, cols, d, cols_total, col_offset);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail_cuda("pips_peer_scatter", e);
 }

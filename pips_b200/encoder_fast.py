@@ -148,13 +148,13 @@ def _packed_weight(conv: torch.nn.Conv2d):
 
 
 class _Pair:
-    """bf16 (hi, lo) channels-last activation (N, H, W, Cp); channels beyond C stay zero."""
+    """bf16 (hi, lo) channels-last activation (N, H, W, Cp); the producing kernel (pips_inorm_apply_pair, pips_resize_pair,
+    pips_stem_pack) writes the padding channels [C, Cp) as zero itself, so no fill pass is needed."""
 
     def __init__(self, N, H, W, C, device):
         self.shape, self.C, self.Cp = (N, H, W), C, _pad64(C)
-        alloc = torch.zeros if self.Cp != C else torch.empty
-        self.hi = alloc(N, H, W, self.Cp, dtype=torch.bfloat16, device=device)
-        self.lo = alloc(N, H, W, self.Cp, dtype=torch.bfloat16, device=device)
+        self.hi = torch.empty(N, H, W, self.Cp, dtype=torch.bfloat16, device=device)
+        self.lo = torch.empty(N, H, W, self.Cp, dtype=torch.bfloat16, device=device)
 
 
 def conv_tc(x: _Pair, conv: torch.nn.Conv2d, bias: bool = False) -> torch.Tensor:

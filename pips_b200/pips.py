@@ -130,6 +130,16 @@ class Pips(nn.Module):
         self._shard = (dist.get_rank(group), dist.get_world_size(group), group)
         return self
 
+    def close_peer_slabs(self) -> None:
+        """Collective: release the peer-mapped slabs of a particle-sharded model (results and feature maps).  They are
+        re-created on demand by the next sharded forward."""
+        for name in ("_peer_slab", "_fmap_peer_slab"):
+            slab = getattr(self, name, None)
+            if slab is not None:
+                slab.close()
+                setattr(self, name, None)
+        self._engine.invalidate(graphs_only=True)
+
     # ------------------------------------------------------------------ forward
     def encode(self, rgbs: torch.Tensor, torch_only: bool = False) -> torch.Tensor:
         """nets/pips.py:436-445: normalise to [-1,1], fnet per frame -> (B,S,128,H8,W8) fp32.

@@ -11,7 +11,8 @@ own full copy of the feature pyramid.  The only exchange is the results (every r
   * ``refine_sharded_nccl``: one asynchronous ``all_gather_into_tensor`` per iteration plus two at the end
     (ranks on different hosts, ``PIPS_B200_GATHER=nccl``, or slab set-up failed -- decided collectively).
 
-``encode_sharded`` splits the encoder's frames over the ranks (one NCCL all-gather of the feature maps).
+``encode_sharded`` splits the encoder's frames over the ranks and exchanges the feature maps the same way
+(peer stores between two flag barriers; NCCL all-gather as the fallback).
 Both paths are bit-identical to the unsharded run (tools/check_sharded.py on 2 / 8 GPUs; the host logic is
 covered by the world-size-2 gloo tests in tests/test_sharding_cpu.py).
 """
@@ -168,11 +169,38 @@ def refine_sharded_nccl(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_i
     return preds_full, vis_full, ff_full
 
 
+def _fmap_slab(model, need_bytes: int, dev):
+    """The peer slab the frame-sharded encoder's feature maps are exchanged through (collective create / regrow).
+    Returns None -- on every rank together -- when the slabs cannot be set up; the caller then uses NCCL."""
+    from . import _lib as L
+    from .peer import PeerSlab
+    rank, world, group = model._shard
+    slab = getattr(model, "_fmap_peer_slab", None)
+    if slab is not None and slab.nbytes >= need_bytes and slab.device == dev:
+        return slab
+    if slab is not None:
+        slab.close()
+    model._fmap_peer_slab = None
+    try:
+        model._fmap_peer_slab = PeerSlab(need_bytes, rank, world, group, dev)
+    except L.PipsCudaError as e:            # raised on every rank together (peer.py)
+        import warnings
+        warnings.warn(f"{e}; exchanging the feature maps with an NCCL all-gather instead")
+        model._fmap_exchange = "nccl"
+    return model._fmap_peer_slab
+
+
 def encode_sharded(model, rgbs: torch.Tensor) -> torch.Tensor:
     """Frame-sharded fnet: the B*S frames are independent (InstanceNorm is per frame,
-    nets/pips.py:412), so rank g encodes frames [g*F/G, (g+1)*F/G) and one all-gather of the channels-last feature
-    maps (<= a few tens of MB over NVLink) replaces G redundant encoder passes.  Bit-identical to the unsharded
-    encoder: every kernel of the 'tc' encoder works per image."""
+    nets/pips.py:412), so rank g encodes frames [g*F/G, (g+1)*F/G) and every rank ends up with all feature maps.
+    Bit-identical to the unsharded encoder: every kernel of the 'tc' encoder works per image.
+
+    Exchange: like the results, through peer-mapped slabs when all ranks share a host -- each rank stores its
+    frames' channels-last maps into every rank's slab over NVLink (``pips_peer_scatter``, 512-byte runs per warp)
+    between two flag barriers (slab reuse / stores landed); no collective library call.  Otherwise (ranks on
+    several hosts, ``PIPS_B200_GATHER=nccl``, set-up failed) one NCCL all-gather."""
+    from . import _lib as L
+    from .peer import FLAG_WORDS
     rank, world, group = model._shard
     B, S, C, H, W = rgbs.shape
     F_ = B * S
@@ -184,7 +212,19 @@ def encode_sharded(model, rgbs: torch.Tensor) -> torch.Tensor:
     _mark("fnet_local")
     H8, W8 = mine.shape[-2:]
     local = mine[0].permute(0, 2, 3, 1).contiguous()                                             # (per, H8, W8, 128)
-    full = torch.empty(world * per, H8, W8, local.shape[-1], dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(full, local, group=group)
-    _mark("fmaps_allgather")
-    return full[:F_].reshape(B, S, H8, W8, -1).permute(0, 1, 4, 2, 3)                            # logical (B,S,128,H8,W8)
+    dev = local.device
+    words = local.numel()                                                                        # per rank
+    mode = (getattr(model, "_fmap_exchange", None) or gather_mode(model)) if local.is_cuda else "nccl"
+    slab = _fmap_slab(model, 4 * (FLAG_WORDS + world * words), dev) if mode == "p2p" else None
+    if slab is None:
+        full = torch.empty(world * per, H8, W8, local.shape[-1], dtype=local.dtype, device=dev)
+        dist.all_gather_into_tensor(full, local, group=group)
+        _mark("fmaps_exchange")
+        return full[:F_].reshape(B, S, H8, W8, -1).permute(0, 1, 4, 2, 3)                        # logical (B,S,128,H8,W8)
+    slab.barrier()                      # every rank has copied the previous call's maps out of its slab
+    L.check(L.load().pips_peer_scatter(L.ptr(local), 1, words, slab.region_ptrs(FLAG_WORDS), world, world * words, rank * words,
+                                       torch.cuda.current_stream(dev).cuda_stream), "pips_peer_scatter")
+    slab.barrier()                      # every rank's stores into this slab have landed
+    full = slab.words[FLAG_WORDS:FLAG_WORDS + world * words].view(world * per, H8, W8, local.shape[-1])[:F_].clone()
+    _mark("fmaps_exchange")
+    return full.reshape(B, S, H8, W8, -1).permute(0, 1, 4, 2, 3)                                 # logical (B,S,128,H8,W8)

@@ -190,11 +190,14 @@ def test_peer_slab_exchange_world1():
                 got = sharding.refine_sharded_p2p(model, fmaps.float(), coords, None, c["iters"], float(c["stride"]))
                 for a, b in zip(ref, got):
                     assert torch.equal(a, b)
+            # the frame-sharded encoder's exchange through its own slab (scatter between two barriers), twice (reuse)
+            for _ in range(2):
+                assert torch.equal(sharding.encode_sharded(model, rgbs).contiguous(), fmaps.contiguous())
             big = coords.repeat(1, 1, 40, 1)                 # more particles: the slab grows (collective re-allocation)
             ref2 = model.engine.refine(model, fmaps.float(), big, None, 2, float(c["stride"]))
             got2 = sharding.refine_sharded_p2p(model, fmaps.float(), big, None, 2, float(c["stride"]))
             assert all(torch.equal(a, b) for a, b in zip(ref2, got2))
-        model._peer_slab.close()
+        model.close_peer_slabs()
     finally:
         model._shard = None
         if created:

@@ -23,5 +23,6 @@ def run(fn, name):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); L.check(fn(*args)); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     ts.sort(); print(f"{name}: median {ts[10]*1e3:.1f} us  min {ts[0]*1e3:.1f} us")
-run(lambda *a: lib.pips_tokenmix(*a, None, st), f"tokenmix simt (occ env={os.environ.get('PIPS_B200_TOKENMIX_OCC','4')})")
-run(lambda *a: lib.pips_tokenmix_tc(*a, st), "tokenmix tc")
+# pips_tokenmix dispatches on PIPS_B200_TOKENMIX (read once per process): "simt" = CUDA-core kernel, default = tensor-core kernel
+run(lambda *a: lib.pips_tokenmix(*a, None, st), f"pips_tokenmix [PIPS_B200_TOKENMIX={os.environ.get('PIPS_B200_TOKENMIX', 'tc (default)')}]")
+run(lambda *a: lib.pips_tokenmix_tc(*a, st), "pips_tokenmix_tc (tensor-core kernel, explicit entry)")

@@ -48,9 +48,7 @@ for name, c in CASES.items():
         torch.cuda.synchronize()
         print(f"rank {rank}/{world} {name} [{mode}]: N={c['N']} sharded==single bit-exact: {same} (max diff {err:.2e}); "
               f"{t0.elapsed_time(t1) / 5:.2f} ms/forward", flush=True)
-        slab = getattr(sharded, "_peer_slab", None)
-        if slab is not None:
-            slab.close()
+        sharded.close_peer_slabs()
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

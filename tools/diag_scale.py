@@ -94,8 +94,6 @@ for mode in ("p2p", "nccl"):
             print(f"--- {mode}, {'host sync per step' if sync_each else 'run-ahead'} ---")
             for r in rows:
                 print(r, flush=True)
-    slab = getattr(model, "_peer_slab", None)
-    if slab is not None:
-        slab.close()
+    model.close_peer_slabs()
 dist.barrier()
 dist.destroy_process_group()

@@ -363,6 +363,7 @@ def test_conv_tc(N, H, W, cin, cout, k, stride, pad, bias):
     conv = torch.nn.Conv2d(cin, cout, k, stride=stride, padding=pad).to(DEV)
     x = torch.randn(N, H, W, cin, device=DEV)
     pair = _Pair(N, H, W, cin, DEV)
+    pair.hi.zero_(); pair.lo.zero_()            # K padding [cin, Cp): in the encoder the producing kernels write it as zero
     hi = x.to(torch.bfloat16)
     pair.hi[..., :cin] = hi
     pair.lo[..., :cin] = (x - hi.float()).to(torch.bfloat16)

@@ -1,6 +1,7 @@
 // C-ABI glue: error state, driver entry points, weight packing and the whole-iteration operators
 // (pips_mixer_forward / pips_refine_iter) that chain the kernels of this library on one stream.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -16,6 +17,15 @@ int fail(const char* msg) {
 int fail_cuda(const char* where, cudaError_t e) {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
     return 2;
+}
+
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("PIPS_B200_PDL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
 }
 
 int current_device() {

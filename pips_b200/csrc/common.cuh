@@ -34,6 +34,30 @@ bool encode_tiled(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, vo
                   const cuuint64_t* gstride_bytes, const cuuint32_t* box, const cuuint32_t* estride,
                   CUtensorMapSwizzle swizzle);
 
+// ---- programmatic dependent launch (PDL).  Kernels of the per-iteration chain are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's CTAs may become resident and run their
+// prologue (barrier init, TMEM allocation, tensor-map prefetch, weight staging into shared memory) while the previous
+// kernel drains; pdl_wait() blocks until every prerequisite grid has completed and its writes are visible, so it must
+// precede the first access to any buffer another kernel of the chain writes (and any global write).  pdl_trigger()
+// (issued at kernel entry) lets the dependent grid be scheduled as soon as all CTAs of this grid have started.
+// RULE: only kernels that call pdl_wait() may be launched through launch_pdl().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();          // PIPS_B200_PDL != "0" (abi.cu)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
     return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
 }

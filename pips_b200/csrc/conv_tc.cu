@@ -37,6 +37,7 @@ struct ConvArgs {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const ConvArgs a) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_RING_BYTES);
@@ -86,6 +87,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                         // the activation operand comes from the previous kernel
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
@@ -264,8 +266,9 @@ static int conv_tc_impl(const void* x_hi, const void* x_lo, int N, int H, int W,
     const int pair_tiles = (total_tiles + 1) / 2;
     const int max_pairs = sm_count() / 2;
     const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
-    conv_tc_kernel<<<2 * pairs, C_THREADS, C_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(ma_hi, ma_lo, mw_hi, mw_lo, a);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(conv_tc_kernel, dim3(2 * pairs), dim3(C_THREADS), C_SMEM_BYTES, static_cast<cudaStream_t>(stream), ma_hi, ma_lo,
+                               mw_hi, mw_lo, a);
+    if (e == cudaSuccess) e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail_cuda("pips_conv_tc: launch", e);
 }
 

@@ -108,6 +108,7 @@ template <typename T>
 __global__ void __launch_bounds__(CG_WARPS * 32)
 corr_gather_kernel(const __grid_constant__ CgMaps maps, const CgArgs a) {
     using Cfg = CgCfg<T>;
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + Cfg::kBoxBytes - 1) &
                                                ~static_cast<uintptr_t>(Cfg::kBoxBytes - 1));
@@ -146,6 +147,7 @@ corr_gather_kernel(const __grid_constant__ CgMaps maps, const CgArgs a) {
         }
     };
 
+    pdl_wait();                                     // coords / ffeats / pyramid come from earlier kernels of the chain
     UnitInfo cur = load_unit(a, u, total);
     UnitInfo nxt = load_unit(a, u + nwarps, total);
     float4 q = *reinterpret_cast<const float4*>(a.ffeats + static_cast<size_t>(u) * 128 + lane * 4);
@@ -277,8 +279,8 @@ static int launch_corr_gather(const void* const* lvl, CUtensorMapDataType dt, co
     long long grid = (units + CG_WARPS - 1) / CG_WARPS;
     const long long cap = static_cast<long long>(sm_count()) * ctas_per_sm;
     if (grid > cap) grid = cap;
-    corr_gather_kernel<T><<<static_cast<unsigned>(grid), CG_WARPS * 32, Cfg::kSmemBytes, st>>>(maps, args);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(corr_gather_kernel<T>, dim3(static_cast<unsigned>(grid)), dim3(CG_WARPS * 32), Cfg::kSmemBytes, st, maps, args);
+    if (e == cudaSuccess) e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail_cuda("pips_corr_gather: launch", e);
 }
 

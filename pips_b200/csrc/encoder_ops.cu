@@ -19,6 +19,8 @@ __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__flo
 __global__ void __launch_bounds__(256)
 inorm_partial_kernel(const float* __restrict__ y, int HW, int C, int chunk_px, float* __restrict__ partial) {
     extern __shared__ float sm[];                       // [rows][2][C]
+    pdl_trigger();
+    pdl_wait();
     const int c4n = C >> 2;
     const int lane_c = threadIdx.x % c4n, row = threadIdx.x / c4n, rows = blockDim.x / c4n;
     const int n = blockIdx.y, chunk = blockIdx.x;
@@ -45,6 +47,8 @@ inorm_partial_kernel(const float* __restrict__ y, int HW, int C, int chunk_px, f
 
 __global__ void inorm_finalize_kernel(const float* __restrict__ partial, int chunks, int HW, int C, float* __restrict__ stats) {
     const int n = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         double s = 0.0, q = 0.0;
         for (int k = 0; k < chunks; ++k) {
@@ -71,6 +75,8 @@ struct ApplyArgs {
 
 __global__ void __launch_bounds__(256)
 inorm_apply_kernel(const ApplyArgs a, size_t total4) {
+    pdl_trigger();
+    pdl_wait();
     const int c4n = a.C >> 2;
     // with a bf16 pair output the loop also covers the pair's padding channels [C, pair_ld) and writes them as zero
     // (they are K padding of the next convolution): no separate fill pass over the operand
@@ -128,6 +134,8 @@ resize_split3_kernel(const float* __restrict__ src, int Hs, int Ws, int C, float
                      __nv_bfloat16* __restrict__ dst_lo, int Ho, int Wo, int Ctot, int c_off, size_t total4) {
     // bf16 pair output: when fewer than 64 channels remain after this slice they are the concat's K padding (rows are padded
     // to a multiple of 64) -- this call writes them as zero, so the concat needs no fill pass
+    pdl_trigger();
+    pdl_wait();
     const int tail = (!dst && Ctot - (c_off + C) < 64) ? Ctot - (c_off + C) : 0;
     const int c4n = (C + tail) >> 2, c4v = C >> 2;
     // at::native area_pixel_compute_scale(align_corners=true): (in - 1) / (out - 1), 0 when out == 1
@@ -183,6 +191,8 @@ __global__ void __launch_bounds__(256)
 stem_pack_kernel(const T* __restrict__ rgb, int H, int W, int Wo, __nv_bfloat16* __restrict__ out_hi,
                  __nv_bfloat16* __restrict__ out_lo, size_t total) {
     // one thread per (n, y, ox, group of 4 channels); 16 groups per pixel, groups 6..15 are zero padding
+    pdl_trigger();
+    pdl_wait();
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const int g = static_cast<int>(i & 15);
         size_t p = i >> 4;
@@ -228,11 +238,11 @@ extern "C" int pips_inorm_stats(const float* y, int N, int HW, int C, float* par
     const int chunk_px = (HW + chunks - 1) / chunks;
     const size_t smem = static_cast<size_t>(rows) * 2 * C * sizeof(float);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    inorm_partial_kernel<<<dim3(chunks, N), 256, smem, st>>>(y, HW, C, chunk_px, partial);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(inorm_partial_kernel, dim3(chunks, N), dim3(256), smem, st, y, HW, C, chunk_px, partial);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail_cuda("pips_inorm_stats: partial", e);
-    inorm_finalize_kernel<<<N, 256, 0, st>>>(partial, chunks, HW, C, stats);
-    e = cudaGetLastError();
+    e = launch_pdl(inorm_finalize_kernel, dim3(N), dim3(256), 0, st, static_cast<const float*>(partial), chunks, HW, C, stats);
+    if (e == cudaSuccess) e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail_cuda("pips_inorm_stats: finalize", e);
 }
 
@@ -248,8 +258,8 @@ static int inorm_apply_impl(const float* y, const float* stats_y, const float* r
     a.out_plain = out_plain; a.out_split = out_split; a.split_ld = split_ld; a.HW = HW; a.C = C;
     a.out_hi = static_cast<__nv_bfloat16*>(out_hi); a.out_lo = static_cast<__nv_bfloat16*>(out_lo); a.pair_ld = pair_ld;
     const size_t total4 = static_cast<size_t>(N) * HW * ((out_hi ? pair_ld : C) / 4);
-    inorm_apply_kernel<<<grid_for(total4), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, total4);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(inorm_apply_kernel, dim3(grid_for(total4)), dim3(256), 0, static_cast<cudaStream_t>(stream), a, total4);
+    if (e == cudaSuccess) e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail_cuda("pips_inorm_apply", e);
 }
 
@@ -273,9 +283,9 @@ static int resize_impl(const float* src, int N, int Hs, int Ws, int C, float* ds
         return fail("pips_resize: bad shape");
     const int tail = (!dst && Ctot - (c_off + C) < 64) ? Ctot - (c_off + C) : 0;
     const size_t total4 = static_cast<size_t>(N) * Ho * Wo * ((C + tail) / 4);
-    resize_split3_kernel<<<grid_for(total4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        src, Hs, Ws, C, dst, static_cast<__nv_bfloat16*>(dst_hi), static_cast<__nv_bfloat16*>(dst_lo), Ho, Wo, Ctot, c_off, total4);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(resize_split3_kernel, dim3(grid_for(total4)), dim3(256), 0, static_cast<cudaStream_t>(stream), src, Hs, Ws, C, dst,
+                               static_cast<__nv_bfloat16*>(dst_hi), static_cast<__nv_bfloat16*>(dst_lo), Ho, Wo, Ctot, c_off, total4);
+    if (e == cudaSuccess) e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail_cuda("pips_resize", e);
 }
 
@@ -297,15 +307,15 @@ extern "C" int pips_stem_pack(const void* rgb, int dtype, int N, int H, int W, v
     const int Wo = (W - 1) / 2 + 1;
     const size_t total = static_cast<size_t>(N) * H * Wo * 16;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype != 0 && dtype != 1) return fail("pips_stem_pack: dtype must be 0 (fp32) or 1 (bf16)");
+    cudaError_t e0;
     if (dtype == 0)
-        stem_pack_kernel<float><<<grid_for(total), 256, 0, st>>>(static_cast<const float*>(rgb), H, W, Wo, static_cast<__nv_bfloat16*>(out_hi),
-                                                                  static_cast<__nv_bfloat16*>(out_lo), total);
-    else if (dtype == 1)
-        stem_pack_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(rgb), H, W, Wo,
-                                                                          static_cast<__nv_bfloat16*>(out_hi),
-                                                                          static_cast<__nv_bfloat16*>(out_lo), total);
+        e0 = launch_pdl(stem_pack_kernel<float>, dim3(grid_for(total)), dim3(256), 0, st, static_cast<const float*>(rgb), H, W, Wo,
+                        static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), total);
     else
-        return fail("pips_stem_pack: dtype must be 0 (fp32) or 1 (bf16)");
+        e0 = launch_pdl(stem_pack_kernel<__nv_bfloat16>, dim3(grid_for(total)), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(rgb), H, W, Wo,
+                        static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), total);
+    if (e0 != cudaSuccess) return fail_cuda("pips_stem_pack", e0);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail_cuda("pips_stem_pack", e);
 }

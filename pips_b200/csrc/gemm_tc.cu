@@ -61,6 +61,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_trigger();
 
     const int tiles_m = (args.M + BM - 1) / BM;
     const int tiles_n = (args.N + BN - 1) / BN;
@@ -94,6 +95,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                             // operands and the residual stream come from the previous kernel
 
     // Register budget per warpgroup: the control warps (0-3) need few, the epilogue warpgroups (4-7, 8-11) many.
     if (warp < 4) {
@@ -305,8 +307,9 @@ static int launch_variant(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, co
     }
     const int tiles = ((args.M + BM - 1) / BM) * ((args.N + BN - 1) / BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    gemm_tc_kernel<TERMS, BN><<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, args);
-    return 0;
+    cudaError_t e = launch_pdl(gemm_tc_kernel<TERMS, BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmemBytes, st, ma_hi, ma_lo, mw_hi, mw_lo, args);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail_cuda("pips_gemm_tc: launch", e);
 }
 
 int launch_single(int bn, bool x3, const void* a_hi, const void* a_lo, int lda, int a_rows, const void* w_hi, const void* w_lo,

@@ -47,6 +47,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const GemmArgs args) {
     using Cfg = PairCfg<TERMS>;
     constexpr int kStages = Cfg::kStages;
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* epi_stage = smem + kStages * Cfg::kStageBytes;
@@ -100,6 +101,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     cluster_sync_all();                                     // barriers + TMEM of both CTAs ready before any remote use
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                             // operands and the residual stream come from the previous kernel
 
     // Register budget per warpgroup: the control warps (0-3) need few, the epilogue warpgroups (4-7, 8-11) many.
     if (warp < 4) {
@@ -261,8 +263,9 @@ static int launch_pair(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const
         args.pair_full_tiles = tiles;
         args.pair_narrow_tiles = 0;
     }
-    gemm_tc2_kernel<TERMS><<<2 * pairs, P_THREADS, Cfg::kSmemBytes, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, mwn_hi, mwn_lo, args);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(gemm_tc2_kernel<TERMS>, dim3(2 * pairs), dim3(P_THREADS), Cfg::kSmemBytes, st, ma_hi, ma_lo, mw_hi, mw_lo,
+                               mwn_hi, mwn_lo, args);
+    if (e == cudaSuccess) e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail_cuda("pips_gemm_tc (pair): launch", e);
 }
 

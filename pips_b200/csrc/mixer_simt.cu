@@ -69,6 +69,7 @@ tokenmix_kernel(float* __restrict__ x, const float* __restrict__ ln1_w, const fl
     // weights duplicated into (w, w) pairs so that one LDS.128 yields two packed FFMA2 operands
     __shared__ __align__(16) float2 s_w1[32 * 8], s_w2t[32 * 8];  // w1[j][s] and w2 transposed to [j][s]
     __shared__ float s_b1[32], s_b2[8];
+    pdl_trigger();
     for (int i = threadIdx.x; i < 256; i += TM_THREADS) {
         s_w1[i] = bcast2(w1[i]);
         s_w2t[(i & 31) * 8 + (i >> 5)] = bcast2(w2[i]);  // w2 is (8 s, 32 j)
@@ -78,6 +79,7 @@ tokenmix_kernel(float* __restrict__ x, const float* __restrict__ ln1_w, const fl
 
     const size_t base = static_cast<size_t>(blockIdx.x) * 8 * 512 + threadIdx.x * 4;
     float xv[8][4], yv[8][4];
+    pdl_wait();                                // x comes from the previous kernel; the weights staged above are constants
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
         const float4 t = *reinterpret_cast<const float4*>(x + base + s * 512);
@@ -143,6 +145,8 @@ ln_pool_kernel(const float* __restrict__ x, const float* __restrict__ ln_w, cons
     __shared__ float red[4][8];
     const size_t base = static_cast<size_t>(blockIdx.x) * 8 * 512 + threadIdx.x * 4;
     float xv[8][4], yv[8][4];
+    pdl_trigger();
+    pdl_wait();
 #pragma unroll
     for (int s = 0; s < 8; ++s) {
         const float4 t = *reinterpret_cast<const float4*>(x + base + s * 512);
@@ -178,10 +182,12 @@ update_kernel(const float* __restrict__ delta, float* __restrict__ coords, const
     float* s_g = sm + 128 * 129;              // [64 rows][132]
     const int rows_total = B * N * S;
     const int r0 = blockIdx.x * UP_ROWS;
-    for (int i = threadIdx.x; i < 128 * 128; i += 256) {
+    pdl_trigger();
+    for (int i = threadIdx.x; i < 128 * 128; i += 256) {      // constant weights: staged while the head GEMM drains
         const int j = i >> 7, k = i & 127;
         s_wt[k * 129 + j] = wu[i];
     }
+    pdl_wait();
     {
         const int lr = threadIdx.x >> 2, part = threadIdx.x & 3;      // 4 threads x 32 channels per row
         const int r = r0 + lr;
@@ -313,8 +319,11 @@ extern "C" int pips_tokenmix(float* x, int seqs, const float* ln1_w, const float
         if (use_tc && y_hi && !y_f32)
             return tokenmix_tc_launch(x, seqs, ln1_w, ln1_b, w1, b1, w2, b2, ln2_w, ln2_b, y_hi, y_lo, static_cast<cudaStream_t>(stream));
     }
-    tokenmix_kernel<<<seqs, TM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, ln1_w, ln1_b, w1, b1, w2, b2, ln2_w, ln2_b, static_cast<__nv_bfloat16*>(y_hi), static_cast<__nv_bfloat16*>(y_lo), y_f32);
+    {
+        cudaError_t e = launch_pdl(tokenmix_kernel, dim3(seqs), dim3(TM_THREADS), 0, static_cast<cudaStream_t>(stream), x, ln1_w, ln1_b, w1, b1,
+                                   w2, b2, ln2_w, ln2_b, static_cast<__nv_bfloat16*>(y_hi), static_cast<__nv_bfloat16*>(y_lo), y_f32);
+        if (e != cudaSuccess) return fail_cuda("pips_tokenmix", e);
+    }
     LAUNCH_CHECK("pips_tokenmix");
     return 0;
 }
@@ -324,8 +333,11 @@ extern "C" int pips_ln_pool(const float* x, int seqs, const float* ln_w, const f
     if (!x || !ln_w || !ln_b) return fail("pips_ln_pool: null pointer");
     if (seqs <= 0) return fail("pips_ln_pool: no sequences");
     if (!p_hi && !p_f32) return fail("pips_ln_pool: no output buffer");
-    ln_pool_kernel<<<seqs, TM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, ln_w, ln_b, static_cast<__nv_bfloat16*>(p_hi), static_cast<__nv_bfloat16*>(p_lo), p_f32);
+    {
+        cudaError_t e = launch_pdl(ln_pool_kernel, dim3(seqs), dim3(TM_THREADS), 0, static_cast<cudaStream_t>(stream), x, ln_w, ln_b,
+                                   static_cast<__nv_bfloat16*>(p_hi), static_cast<__nv_bfloat16*>(p_lo), p_f32);
+        if (e != cudaSuccess) return fail_cuda("pips_ln_pool", e);
+    }
     LAUNCH_CHECK("pips_ln_pool");
     return 0;
 }
@@ -360,8 +372,11 @@ extern "C" int pips_update_peer(const float* delta, float* coords, const float* 
         cudaError_t e = ensure_dyn_smem(update_kernel, attr, static_cast<int>(smem));
         if (e != cudaSuccess) return fail_cuda("pips_update: smem attribute", e);
     }
-    update_kernel<<<(rows + UP_ROWS - 1) / UP_ROWS, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-        delta, coords, coords0, ffeats, gn_w, gn_b, wu, bu, out_px, stride, B, S, N, po);
+    {
+        cudaError_t e = launch_pdl(update_kernel, dim3((rows + UP_ROWS - 1) / UP_ROWS), dim3(256), smem, static_cast<cudaStream_t>(stream),
+                                   delta, coords, coords0, ffeats, gn_w, gn_b, wu, bu, out_px, stride, B, S, N, po);
+        if (e != cudaSuccess) return fail_cuda("pips_update", e);
+    }
     LAUNCH_CHECK("pips_update");
     return 0;
 }

@@ -166,6 +166,7 @@ tokenmix_tc_kernel(float* __restrict__ x, int seqs, const float* __restrict__ ln
                    const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
                    const float* __restrict__ b2, const float* __restrict__ ln2_w, const float* __restrict__ ln2_b,
                    __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
     const uint32_t sbase = smem_u32(smem);
@@ -218,6 +219,7 @@ tokenmix_tc_kernel(float* __restrict__ x, int seqs, const float* __restrict__ ln
     constexpr uint32_t idesc2 = umma_idesc_bf16(128, 16);
     const uint64_t d_b1a = umma_desc_nosw(sbase + TT_OFF_B1A, 128, 256), d_b1b = umma_desc_nosw(sbase + TT_OFF_B1B, 128, 256);
 
+    pdl_wait();                                             // x is written by the previous kernel (weights above are constants)
     // x of the track after the current one is fetched into registers while the current track's GELU phase runs; the
     // current x is dropped after LayerNorm 1 and re-read (an L2 hit) for the residual, so that both fit 128 registers
     float4 nx[8];
@@ -367,9 +369,9 @@ int tokenmix_tc_launch(float* x, int seqs, const float* ln1_w, const float* ln1_
     }
     const int cap = TT_CTAS_PER_SM * sm_count();
     const int grid = seqs < cap ? seqs : cap;
-    tokenmix_tc_kernel<<<grid, TT_THREADS, TT_SMEM, st>>>(x, seqs, ln1_w, ln1_b, w1, b1, w2, b2, ln2_w, ln2_b,
-                                                          static_cast<__nv_bfloat16*>(y_hi), static_cast<__nv_bfloat16*>(y_lo));
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_pdl(tokenmix_tc_kernel, dim3(grid), dim3(TT_THREADS), TT_SMEM, st, x, seqs, ln1_w, ln1_b, w1, b1, w2, b2, ln2_w,
+                               ln2_b, static_cast<__nv_bfloat16*>(y_hi), static_cast<__nv_bfloat16*>(y_lo));
+    if (e == cudaSuccess) e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail_cuda("pips_tokenmix (tc): launch", e);
 }
 

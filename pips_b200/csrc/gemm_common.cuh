@@ -72,7 +72,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& args, const uint3
                 uint32_t hw[4], lw[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float2 g = gelu_fast2(make_float2(f[8 * p + 2 * e], f[8 * p + 2 * e + 1]));
+                    const float2 g = gelu_fast2_abs(make_float2(f[8 * p + 2 * e], f[8 * p + 2 * e + 1]));
                     hw[e] = cvt_bf16x2(g.x, g.y);
                     const float2 lo = fma2(make_float2(__uint_as_float(hw[e] << 16), __uint_as_float(hw[e] & 0xffff0000u)),
                                            bcast2(-1.0f), g);                       // g - hi, one rounding

@@ -110,22 +110,29 @@ class PeerSlab:
 
 
 class PeerPlan:
-    """Where one forward's results go inside the slabs: handed to RefineEngine.refine(peer=...)."""
+    """Where one forward's results go inside the slabs: handed to RefineEngine.refine(peer=...).
+    Equal shards of ``per`` particles (the tail padded), or -- ``sizes`` given -- one shard of ``sizes[r]`` particles
+    per rank laid out back to back (speed-weighted sharding, no padding)."""
 
-    def __init__(self, slab: PeerSlab, iters: int, B: int, S: int, per: int):
+    def __init__(self, slab: PeerSlab, iters: int, B: int, S: int, per: int, sizes: Optional[List[int]] = None):
         self.slab = slab
         self.iters, self.B, self.S, self.per = iters, B, S, per
-        self.n_total = per * slab.world
-        self.n_offset = per * slab.rank
+        if sizes is None:
+            self.n_total = per * slab.world
+            self.n_offset = per * slab.rank
+        else:
+            assert len(sizes) == slab.world and sizes[slab.rank] == per
+            self.n_total = int(sum(sizes))
+            self.n_offset = int(sum(sizes[:slab.rank]))
         self.off_coords = FLAG_WORDS
         self.off_vis = self.off_coords + iters * B * S * self.n_total * 2
         self.off_ffeat = self.off_vis + B * S * self.n_total
         self.words = self.off_ffeat + B * self.n_total * LATENT
-        self.key = (slab.generation, slab.local, tuple(slab.ptrs), iters, B, S, per)
+        self.key = (slab.generation, slab.local, tuple(slab.ptrs), iters, B, S, per, self.n_total, self.n_offset)
 
     @staticmethod
-    def words_needed(world: int, iters: int, B: int, S: int, per: int) -> int:
-        nt = per * world
+    def words_needed(world: int, iters: int, B: int, S: int, per: int, n_total: Optional[int] = None) -> int:
+        nt = per * world if n_total is None else n_total
         return FLAG_WORDS + iters * B * S * nt * 2 + B * S * nt + B * nt * LATENT
 
     def coord_bases(self, it: int) -> List[int]:

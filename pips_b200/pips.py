@@ -122,12 +122,22 @@ class Pips(nn.Module):
     def engine(self) -> RefineEngine:
         return self._engine
 
-    def shard_particles(self, group=None) -> "Pips":
-        """Particle-axis data parallelism: every rank owns N/G tracks and a
-        full copy of the feature pyramid; outputs are all-gathered so each rank returns the full
-        result.  Call after ``torch.distributed.init_process_group``."""
+    def shard_particles(self, group=None, balance: Optional[bool] = None) -> "Pips":
+        """Particle-axis data parallelism: every rank owns a share of the tracks and a
+        full copy of the feature pyramid; results are exchanged so each rank returns the full
+        result.  Call after ``torch.distributed.init_process_group``.
+        ``balance`` (default on; PIPS_B200_BALANCE=0 turns it off): after a few forwards the shares become proportional to
+        each GPU's measured speed (sharding._Balance) -- under the power cap the GPUs of a box run at different clocks and
+        a forward is as slow as its slowest rank.  Results do not depend on the shares (tracks are independent)."""
         import torch.distributed as dist
         self._shard = (dist.get_rank(group), dist.get_world_size(group), group)
+        if balance is None:
+            balance = os.environ.get("PIPS_B200_BALANCE", "1") != "0"
+        if balance and self._shard[1] > 1:
+            from .sharding import _Balance
+            self._balance = _Balance()
+        else:
+            self._balance = None
         return self
 
     def close_peer_slabs(self) -> None:

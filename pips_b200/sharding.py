@@ -79,6 +79,60 @@ def refine_sharded(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_init: 
     return refine_sharded_nccl(model, fmaps, coords, feat_init, iters, stride)
 
 
+def shard_sizes(N: int, weights, quantum: int = 32):
+    """Speed-weighted shard sizes: ``weights[r]`` ~ particles per second of rank r.  Sizes are multiples of ``quantum``
+    tracks (32 tracks = one 256-row GEMM tile) where N allows, at least 1, and sum to N.  Deterministic in its inputs,
+    so every rank computes the same list."""
+    world = len(weights)
+    if N < world:
+        return None
+    q = quantum if N >= 4 * quantum * world else 1
+    tot = float(sum(weights))
+    ideal = [N * w / tot for w in weights]
+    sizes = [max(1 if q == 1 else q, int(x // q) * q) for x in ideal]
+    # hand the remainder out in quantum steps to the ranks furthest below their ideal share (ties: lowest rank)
+    while sum(sizes) > N:
+        r = max(range(world), key=lambda i: (sizes[i] - ideal[i], -i))
+        sizes[r] -= min(q, sum(sizes) - N)
+    while sum(sizes) < N:
+        r = min(range(world), key=lambda i: (sizes[i] - ideal[i], i))
+        sizes[r] += min(q, N - sum(sizes))
+    return sizes if min(sizes) >= 1 else None
+
+
+class _Balance:
+    """Speed-weighted particle shards.  The GPUs of one box do not run at one clock under the power cap (1.47-1.78 GHz
+    seen on 8 B200s), and every forward ends in an exchange of results, so with equal shards the step time is the
+    SLOWEST GPU's.  After ``warm`` sharded forwards each rank times ``measure`` refinement calls with CUDA events, the
+    rates (particles per second) are exchanged once, and from then on rank r gets a share proportional to its rate."""
+
+    def __init__(self, warm: int = 2, measure: int = 3):
+        self.warm, self.measure = warm, measure
+        self.calls, self.events, self.weights = 0, [], None
+
+    def before(self):
+        self.calls += 1
+        if self.weights is None and self.calls > self.warm:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            return ev
+        return None
+
+    def after(self, ev, n_particles: int, group) -> None:
+        if ev is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.events.append((ev, e1, n_particles))
+        if len(self.events) >= self.measure:               # same call count on every rank: collective below is matched
+            torch.cuda.synchronize()
+            rate = sum(n for _, _, n in self.events) / max(1e-6, sum(a.elapsed_time(b) for a, b, _ in self.events))
+            rates = [None] * dist.get_world_size(group)
+            dist.all_gather_object(rates, float(rate), group=group)
+            self.weights = rates
+            self.events = []
+
+
 def refine_sharded_p2p(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_init: Optional[torch.Tensor], iters: int,
                        stride: float):
     """No collective on the data path: every rank's update kernel writes its predictions into all ranks' result
@@ -88,8 +142,12 @@ def refine_sharded_p2p(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_in
     rank, world, group = model._shard
     B, S, N, _ = coords.shape
     n0, n1, per = shard_bounds(N, rank, world)
+    bal = getattr(model, "_balance", None)
+    sizes = shard_sizes(N, bal.weights) if (bal is not None and bal.weights is not None) else None
+    if sizes is not None:                                                   # speed-weighted shards, no padding
+        n0 = sum(sizes[:rank]); n1 = n0 + sizes[rank]; per = sizes[rank]
     dev = coords.device
-    need = 4 * PeerPlan.words_needed(world, iters, B, S, per)
+    need = 4 * PeerPlan.words_needed(world, iters, B, S, per, None if sizes is None else N)
     slab = getattr(model, "_peer_slab", None)
     if slab is None or slab.nbytes < need or slab.device != dev:           # collective: all ranks see the same shapes
         grown = 0
@@ -105,14 +163,17 @@ def refine_sharded_p2p(model, fmaps: torch.Tensor, coords: torch.Tensor, feat_in
             warnings.warn(f"{e}; exchanging results with NCCL all-gathers instead")
             model._gather_mode = "nccl"
             return refine_sharded_nccl(model, fmaps, coords, feat_init, iters, stride)
-    plan = PeerPlan(slab, iters, B, S, per)
+    plan = PeerPlan(slab, iters, B, S, per, sizes)
     my_coords = _pad_particles(coords[:, :, n0:n1], 2, per)
     my_feat = None if feat_init is None else _pad_particles(feat_init[:, n0:n1], 1, per)
 
     _mark("inputs")
     slab.barrier()                      # every rank has copied the previous call's results out of its slab
     _mark("barrier0")
+    ev = bal.before() if bal is not None else None
     _, vis, ffeat = model.engine.refine(model, fmaps, my_coords, my_feat, iters, stride, peer=plan)
+    if bal is not None:
+        bal.after(ev, B * per, group)
     _mark("refine")
     lib, st = L.load(), torch.cuda.current_stream(dev).cuda_stream
     vis, ffeat = vis.contiguous(), ffeat.contiguous()

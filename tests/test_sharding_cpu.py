@@ -88,3 +88,17 @@ def test_refine_sharded_world2_gloo(N, use_feat):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
     assert all(shape == (3, 2, 8, N, 2) for _, _, shape in res)
+
+
+def test_speed_weighted_shard_sizes():
+    """sharding.shard_sizes: deterministic, sums to N, every rank gets work, proportional to the measured rates, whole
+    32-track GEMM tiles where N allows."""
+    from pips_b200.sharding import shard_sizes
+    rates = [1.0, 1.1, 0.9, 1.0, 1.05, 0.95, 1.0, 1.0]
+    sz = shard_sizes(8192, rates)
+    assert sum(sz) == 8192 and all(s % 32 == 0 for s in sz) and sz == shard_sizes(8192, list(rates))
+    assert sz[1] > sz[0] > sz[2] and abs(sz[1] / 8192 - 1.1 / 8.0) < 0.01
+    assert shard_sizes(17, [1, 1, 1, 1]) == [5, 4, 4, 4]                  # small N: single tracks, still sums to N
+    assert sum(shard_sizes(20, [1.0, 1.2])) == 20 and shard_sizes(20, [1.0, 1.2])[1] > 10
+    assert shard_sizes(3, [1, 1, 1, 1]) is None                           # fewer particles than ranks: equal padded shards
+    assert sum(shard_sizes(4097, [3.0, 1.0])) == 4097 and min(shard_sizes(4097, [30.0, 1.0])) >= 1

@@ -31,7 +31,8 @@ for name, c in CASES.items():
         sharded = synthetic.seeded_model(stride=c["stride"], seed=3).to(dev).eval()
         sharded.shard_particles()
         sharded._gather_mode = mode
-        for rep in range(3):                # repeated calls reuse the slab: the barriers must fence it
+        for rep in range(8):                # repeated calls reuse the slab (the barriers must fence it); after the 5th the
+                                            # shards are speed-weighted (sharding._Balance): uneven sizes, still bit-exact
             with torch.no_grad():
                 b = sharded(xys.to(dev), rgbs.to(dev), iters=c["iters"], return_feat=True, **extra)
             same = all(torch.equal(x, y) for x, y in zip(a[0], b[0])) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])

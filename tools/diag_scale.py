@@ -19,7 +19,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-B, S, H, W, NPER, ITERS, STEPS = 4, 8, 384, 512, 1024, 6, 10
+B, S, H, W, NPER, ITERS, STEPS = 4, 8, 384, 512, 1024, 6, 25
 rgbs = synthetic.smooth_video(B, S, H, W, seed=1234).to(torch.bfloat16).to(dev)
 xys = synthetic.random_queries(B, NPER * world, H, W, seed=4321).to(dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -74,9 +74,13 @@ for mode in ("p2p", "nccl"):
     model = synthetic.seeded_model(stride=8, seed=0).to(dev).eval()
     model.shard_particles()
     model._gather_mode = mode
-    for _ in range(3):
+    for _ in range(8):                                   # > the 5 calls after which the shards become speed-weighted
         with torch.no_grad():
             model(xys, rgbs, iters=ITERS)
+    bal = getattr(model, "_balance", None)
+    if rank == 0:
+        print(f"=== {mode}: shard sizes", sharding.shard_sizes(NPER * world, bal.weights) if bal is not None and bal.weights else "equal",
+              "rates (particles/ms)", [round(w, 1) for w in bal.weights] if bal is not None and bal.weights else None, flush=True)
     for sync_each in (False, True):
         dist.barrier()
         torch.cuda.synchronize()

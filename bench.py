@@ -371,7 +371,10 @@ def run_ours(args, rank, world, local_rank):
         per = [a.elapsed_time(b) for a, b in evs]
         return sum(per) / 1e3, per
 
-    for _ in range(max(3, args.warmup)):
+    # sharded runs: the particle shares become speed-weighted after the 5th forward (pips_b200/sharding.py::_Balance) and the
+    # next forward re-captures its CUDA graph at the new share -- all of that belongs to the warm-up
+    n_warm = max(3, args.warmup) if world == 1 else max(8, args.warmup)
+    for _ in range(n_warm):
         step_device()
     barrier()
     sampler = ClockSampler(dev)                      # every rank watches its own GPU
@@ -409,6 +412,7 @@ def run_ours(args, rank, world, local_rank):
             m = synthetic.seeded_model(stride=stride, seed=0, head_scale=0.05, precision=args.precision, feat_dtype=args.feat).to(dev).eval()
             if world > 1:
                 m.shard_particles()
+                m._balance = model._balance             # the GPUs' measured rates carry over: no second calibration
             return m
 
         if world == 1:
@@ -428,6 +432,10 @@ def run_ours(args, rank, world, local_rank):
 
     updates = B * S * n_global * ITERS
     pk = peaks()
+    shard_sizes_now = None
+    if world > 1 and getattr(model, "_balance", None) is not None and model._balance.weights:
+        from pips_b200.sharding import shard_sizes
+        shard_sizes_now = shard_sizes(n_global, model._balance.weights)
     # per-kernel timing of one iteration, live, same buffers (CUDA events around every launch)
     with torch.no_grad():
         fmaps = model.encode(rgbs)
@@ -490,11 +498,11 @@ def run_ours(args, rank, world, local_rank):
     h2d = rgbs_h.numel() * rgbs_h.element_size() + xys_h.numel() * 4
     d2h = (B * S * n_global * 2 + B * S * n_global) * 4
     line = {"metric": METRIC, "value": updates / (t_dev / args.steps), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": n_warm, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (hi/lo split, fp32 accumulate) + f32", "bf16": "bf16"}[args.precision],
             "data": "synthetic",
             "config": {"workload": workload_name(world),
-                       "precision": args.precision, "feat_dtype": args.feat, "parallelism": f"particle-sharded dp{world}" if world > 1 else "single GPU",
+                       "precision": args.precision, "feat_dtype": args.feat, "parallelism": (f"particle-sharded dp{world}, shares " + ("speed-weighted " + str(shard_sizes_now) if shard_sizes_now else "equal")) if world > 1 else "single GPU",
                        "includes": "fnet (tcgen05 convs) + pyramid + 6 refinement iterations + vis head", "fnet_mode": model.fnet_mode, "l2": "256 MB write between steps (L2 flushed); working set > L2"},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": updates / (t_e2e / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -6,7 +6,7 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr
 timeout 600 $TR tools/check_sharded.py > gpurun_out/${tag}_check_sharded_${G}.log 2>&1; echo "check_sharded rc=$?"
 grep -E "bit-exact" gpurun_out/${tag}_check_sharded_${G}.log | grep "rank 0" | head -8
 timeout 600 $TR tools/diag_scale.py > gpurun_out/${tag}_diag_${G}.log 2>&1; echo "diag rc=$?"
-grep -E "^---|^\{" gpurun_out/${tag}_diag_${G}.log | head -40
+grep -E "^---|^\{|^===" gpurun_out/${tag}_diag_${G}.log | head -44
 if [ "$3" == "bench" ]; then
   timeout 900 $TR bench.py --gpus $G --steps 20 --warmup 5 > gpurun_out/${tag}_bench_${G}gpu.json 2> gpurun_out/${tag}_bench_${G}gpu.err; echo "bench rc=$?"
   python - <<PY

@@ -73,6 +73,12 @@ class ClockSampler:
                 pass
             time.sleep(0.1)
 
+    def mark(self):
+        """Forget the samples taken so far (warm-up): the record covers the timed region only."""
+        self.mhz, self.mask = [], 0
+        if self.smi is not None:
+            self.lines = []
+
     def start(self):
         try:
             import pynvml as nv
@@ -374,11 +380,15 @@ def run_ours(args, rank, world, local_rank):
     # sharded runs: the particle shares become speed-weighted after the 5th forward (pips_b200/sharding.py::_Balance) and the
     # next forward re-captures its CUDA graph at the new share -- all of that belongs to the warm-up
     n_warm = max(3, args.warmup) if world == 1 else max(8, args.warmup)
+    # The clock sampler is started BEFORE the warm-up: NVML initialisation in 8 processes at once stalls the driver for
+    # ~0.1 s, and when that fell into the first timed step (round 1 / r02i: one 120 ms step among twenty 38 ms ones) the
+    # device-timed mean came out above the e2e mean.  Samples taken during the warm-up are dropped by mark().
+    sampler = ClockSampler(dev)                      # every rank watches its own GPU
+    sampler.start()
     for _ in range(n_warm):
         step_device()
     barrier()
-    sampler = ClockSampler(dev)                      # every rank watches its own GPU
-    sampler.start()
+    sampler.mark()
     t_dev, per_dev = timed(step_device, args.steps)
     barrier()
     clocks = sampler.stop()

@@ -126,13 +126,15 @@ class Pips(nn.Module):
         """Particle-axis data parallelism: every rank owns a share of the tracks and a
         full copy of the feature pyramid; results are exchanged so each rank returns the full
         result.  Call after ``torch.distributed.init_process_group``.
-        ``balance`` (default on; PIPS_B200_BALANCE=0 turns it off): after a few forwards the shares become proportional to
-        each GPU's measured speed (sharding._Balance) -- under the power cap the GPUs of a box run at different clocks and
-        a forward is as slow as its slowest rank.  Results do not depend on the shares (tracks are independent)."""
+        ``balance`` (default off; PIPS_B200_BALANCE=1 turns it on): after a few forwards the shares become proportional to
+        each GPU's measured speed (sharding._Balance).  Measured on 8 B200s (profiles/r02_diag_8gpu.txt): under the power
+        cap a GPU's speed drifts by +-3-5 % from step to step and WHICH GPU is slowest changes between runs, so a share
+        fixed from a few samples does not beat equal shares -- kept as an option for boxes with a persistently slow GPU.
+        Results do not depend on the shares (tracks are independent): bit-exact either way (tools/check_sharded.py)."""
         import torch.distributed as dist
         self._shard = (dist.get_rank(group), dist.get_world_size(group), group)
         if balance is None:
-            balance = os.environ.get("PIPS_B200_BALANCE", "1") != "0"
+            balance = os.environ.get("PIPS_B200_BALANCE", "0") == "1"
         if balance and self._shard[1] > 1:
             from .sharding import _Balance
             self._balance = _Balance()

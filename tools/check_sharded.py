@@ -29,7 +29,7 @@ for name, c in CASES.items():
         a = single(xys.to(dev), rgbs.to(dev), iters=c["iters"], return_feat=True, **extra)
     for mode in ("p2p", "nccl"):            # peer-mapped slabs (stores fused into the update kernel) / NCCL all-gathers
         sharded = synthetic.seeded_model(stride=c["stride"], seed=3).to(dev).eval()
-        sharded.shard_particles()
+        sharded.shard_particles(balance=True)     # speed-weighted shares after the 5th call: uneven shards must be bit-exact too
         sharded._gather_mode = mode
         for rep in range(8):                # repeated calls reuse the slab (the barriers must fence it); after the 5th the
                                             # shards are speed-weighted (sharding._Balance): uneven sizes, still bit-exact

@@ -72,7 +72,7 @@ def loop(model, sync_each):
 
 for mode in ("p2p", "nccl"):
     model = synthetic.seeded_model(stride=8, seed=0).to(dev).eval()
-    model.shard_particles()
+    model.shard_particles(balance=os.environ.get("PIPS_B200_BALANCE", "0") == "1")
     model._gather_mode = mode
     for _ in range(8):                                   # > the 5 calls after which the shards become speed-weighted
         with torch.no_grad():

@@ -451,6 +451,16 @@ def run_ours(args, rank, world, local_rank):
         fmaps = model.encode(rgbs)
         coords = (xys[:, :N_PER_GPU] / STRIDE).reshape(B, 1, N_PER_GPU, 2).repeat(1, S, 1, 1)
         prof, dims = model.engine.profile_iteration(model, fmaps.float(), coords, STRIDE, reps=3)
+    # the encoder alone (its CUDA graph), same inputs, L2 flushed before each replay
+    fnet_ms = []
+    with torch.no_grad():
+        for _ in range(2):
+            model.encode(rgbs)
+        for _ in range(8):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); model.encode(rgbs); e1.record(); torch.cuda.synchronize()
+            fnet_ms.append(e0.elapsed_time(e1))
     mean = {k: statistics.mean(v) for k, v in prof.items()}
     per_iter = {k: sum(v) / 3 for k, v in prof.items()}
     M = dims["M"]
@@ -519,6 +529,8 @@ def run_ours(args, rank, world, local_rank):
                     "ms_per_step": t_e2e / args.steps * 1e3},
             "roofline": roofline, "roofline_corr": roofline_corr,
             "kernel_ms_per_iteration": {k: round(v, 4) for k, v in per_iter.items()},
+            "fnet_ms": {"median": round(statistics.median(fnet_ms), 3), "min": round(min(fnet_ms), 3), "frames": B * S,
+                        "what": "BasicEncoder on all B*S frames of this rank's batch (unsharded), one CUDA-graph replay"},
             "loop_only": {"ms_per_iteration": sum(per_iter.values()), "updates_per_s": B * S * N_PER_GPU / (sum(per_iter.values()) * 1e-3)},
             "whole_path_tensor_frac": (updates * UNIT_FLOP / (t_dev / args.steps)) / 1e12 / pk["bf16_tflops_sustained"] / world}
     line["ms_per_step_stats_rank0"] = {"device_loop": _stats(per_dev), "e2e_loop": _stats(per_e2e)}

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PIPS_B200_ABI_VERSION 2
+#define PIPS_B200_ABI_VERSION 3
 
 enum { PIPS_S = 8, PIPS_C = 128, PIPS_LEVELS = 4, PIPS_RADIUS = 3 };
 enum { PIPS_KITCHEN = 519, PIPS_KITCHEN_PAD = 576, PIPS_DIM = 512, PIPS_HIDDEN = 2048, PIPS_DEPTH = 12, PIPS_HEAD = 1040 };
@@ -180,8 +180,10 @@ int pips_conv_tc(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp
 int pips_conv_tc_aniso(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp, const void* w_hi, const void* w_lo,
                        int Cout, int R, int S, int stride_y, int stride_x, int pad_y, int pad_x, const float* bias, float* out,
                        void* stream);
-/* nets/pips.py:436 + the column unfolding of the 7x7/2 stem (:206): rgb (N,3,H,W) fp32 (dtype 0) or bf16 (dtype 1),
- * 0..255 -> (N, H, Wo, 64) bf16 (hi, lo), channel k = s*3 + colour holds 2*(rgb/255)-1 at x = 2*ox + s - 3. */
+/* nets/pips.py:436 + the unfolding of the 7x7/2 stem (:206) into a 4x1 stride-1 convolution: rgb (N,3,H,W) fp32
+ * (dtype 0) or bf16 (dtype 1), 0..255 -> (N, Ho+3, Wo, 64) bf16 (hi, lo), Ho = (H-1)/2+1, Wo = (W-1)/2+1; pixel (j, ox)
+ * holds input rows y = 2j-3 (channels 0..31) and y = 2j-2 (channels 32..63), channel k = s*3 + colour of a row =
+ * 2*(rgb/255)-1 at x = 2*ox + s - 3, zero outside the image / for k >= 21.  (ABI 3; ABI 2 unfolded the columns only.) */
 int pips_stem_pack(const void* rgb, int dtype, int N, int H, int W, void* out_hi, void* out_lo, void* stream);
 
 /* Whole-iteration operator: everything between `for itr in range(iters)` and the append of

@@ -183,28 +183,34 @@ resize_split3_kernel(const float* __restrict__ src, int Hs, int Ws, int C, float
 }
 
 // ---------------------------------------------------------------------------------------- stem input
-// nets/pips.py:436 (2*(rgb/255)-1) fused with the column unfolding of the 7x7 / stride-2 stem (:206): for every
-// input row y and output column ox the 7 taps x 3 colours at x = 2*ox + s - 3 (zero outside the image) become 21
-// channels of a 64-channel bf16 (hi, lo) pixel; the stem is then a 7x1 convolution with row stride 2.
+// nets/pips.py:436 (2*(rgb/255)-1) fused with the unfolding of the 7x7 / stride-2 stem (:206) into a plain stride-1
+// convolution with 4 row taps over 64-channel pixels.  Output pixel (j, ox) of the unfolded tensor holds, for the TWO
+// input rows y = 2j-3 and y = 2j-2, the 7 column taps x 3 colours at x = 2*ox + s - 3 (zero outside the image):
+//   channels [ 0,32): row 2j-3, k = s*3 + colour (21 used)      channels [32,64): row 2j-2, same order
+// Output row oy of the stem needs input rows 2oy-3 .. 2oy+3 = row pairs j = oy .. oy+3 (the 8th row, 2oy+4, meets a zero
+// filter row), i.e. a 4x1 convolution with stride 1 and no padding over the (Ho+3) x Wo unfolded image: K = 4 x 64 = 256.
+// (Round 1 unfolded only the columns: one 64-channel pixel per input row, 7 row taps at stride 2 -- K = 448 and twice
+// the bytes; the unfolded tensor is the largest activation of the whole encoder.)
 template <typename T>
 __global__ void __launch_bounds__(256)
-stem_pack_kernel(const T* __restrict__ rgb, int H, int W, int Wo, __nv_bfloat16* __restrict__ out_hi,
+stem_pack_kernel(const T* __restrict__ rgb, int H, int W, int Wo, int J, __nv_bfloat16* __restrict__ out_hi,
                  __nv_bfloat16* __restrict__ out_lo, size_t total) {
-    // one thread per (n, y, ox, group of 4 channels); 16 groups per pixel, groups 6..15 are zero padding
+    // one thread per (n, j, ox, group of 4 channels); 16 groups per pixel: 8 per input row, groups 5 (partly), 6, 7 are padding
     pdl_trigger();
     pdl_wait();
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const int g = static_cast<int>(i & 15);
         size_t p = i >> 4;
         const int ox = static_cast<int>(p % Wo); p /= Wo;
-        const int y = static_cast<int>(p % H);
-        const size_t n = p / H;
+        const int j = static_cast<int>(p % J);
+        const size_t n = p / J;
+        const int y = 2 * j - 3 + (g >> 3);
         __nv_bfloat16 h[4], l[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const int k = g * 4 + e;                     // k = s*3 + colour
+            const int k = (g & 7) * 4 + e;               // k = s*3 + colour
             float v = 0.f;
-            if (k < 21) {
+            if (k < 21 && y >= 0 && y < H) {
                 const int s = k / 3, c = k - 3 * s;
                 const int x = 2 * ox + s - 3;
                 if (x >= 0 && x < W) {
@@ -300,20 +306,21 @@ extern "C" int pips_resize_pair(const float* src, int N, int Hs, int Ws, int C, 
     return resize_impl(src, N, Hs, Ws, C, nullptr, dst_hi, dst_lo, Ho, Wo, Ctot, c_off, stream);
 }
 
-// rgb: (N, 3, H, W) fp32 (dtype 0) or bf16 (dtype 1), values 0..255; out_hi/out_lo: (N, H, Wo, 64) with Wo = (W - 1) / 2 + 1
+// rgb: (N, 3, H, W) fp32 (dtype 0) or bf16 (dtype 1), values 0..255; out_hi/out_lo: (N, Ho + 3, Wo, 64) with
+// Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1
 extern "C" int pips_stem_pack(const void* rgb, int dtype, int N, int H, int W, void* out_hi, void* out_lo, void* stream) {
     if (!rgb || !out_hi || !out_lo) return fail("pips_stem_pack: null pointer");
     if (N <= 0 || H <= 0 || W <= 0) return fail("pips_stem_pack: empty image");
-    const int Wo = (W - 1) / 2 + 1;
-    const size_t total = static_cast<size_t>(N) * H * Wo * 16;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (dtype != 0 && dtype != 1) return fail("pips_stem_pack: dtype must be 0 (fp32) or 1 (bf16)");
+    const int Wo = (W - 1) / 2 + 1, J = (H - 1) / 2 + 1 + 3;
+    const size_t total = static_cast<size_t>(N) * J * Wo * 16;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e0;
     if (dtype == 0)
-        e0 = launch_pdl(stem_pack_kernel<float>, dim3(grid_for(total)), dim3(256), 0, st, static_cast<const float*>(rgb), H, W, Wo,
+        e0 = launch_pdl(stem_pack_kernel<float>, dim3(grid_for(total)), dim3(256), 0, st, static_cast<const float*>(rgb), H, W, Wo, J,
                         static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), total);
     else
-        e0 = launch_pdl(stem_pack_kernel<__nv_bfloat16>, dim3(grid_for(total)), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(rgb), H, W, Wo,
+        e0 = launch_pdl(stem_pack_kernel<__nv_bfloat16>, dim3(grid_for(total)), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(rgb), H, W, Wo, J,
                         static_cast<__nv_bfloat16*>(out_hi), static_cast<__nv_bfloat16*>(out_lo), total);
     if (e0 != cudaSuccess) return fail_cuda("pips_stem_pack", e0);
     cudaError_t e = cudaGetLastError();

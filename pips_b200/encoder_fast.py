@@ -185,16 +185,16 @@ def _apply_pair(ops: _Ops, y, stats, r=None, stats_r=None, relu_main=True, relu_
 
 
 def _packed_stem_weight(conv: torch.nn.Conv2d):
-    """7x7x3 stem (Cout,3,7,7) -> (64, 7*64) bf16 (hi, lo): row tap r major, then k = s*3 + colour (21 of 64 used) --
-    the layout pips_stem_pack unfolds the image into."""
+    """7x7x3 stem (Cout,3,7,7) -> (64, 4*64) bf16 (hi, lo) for the 4x1 convolution over pips_stem_pack's row-pair pixels:
+    tap d (row pair) major, then [filter row 2d: k = s*3 + colour, 21 of 32 | filter row 2d+1: same; row 7 does not exist: 0]."""
     w = conv.weight
     key = (w.data_ptr(), w._version)
     if getattr(conv, "_wstem_key", None) != key:
         lib = L.load()
         cout = w.shape[0]
-        packed = torch.zeros(64, 7, 64, dtype=torch.float32, device=w.device)
-        packed[:cout, :, :21] = w.detach().float().permute(0, 2, 3, 1).reshape(cout, 7, 21)      # [co][r][s*3+ci]
-        packed = packed.reshape(64, 7 * 64).contiguous()
+        rows = torch.zeros(64, 8, 32, dtype=torch.float32, device=w.device)                    # [co][filter row r][s*3+ci]
+        rows[:cout, :7, :21] = w.detach().float().permute(0, 2, 3, 1).reshape(cout, 7, 21)
+        packed = rows.reshape(64, 4 * 64).contiguous()                                          # (r = 2d, 2d+1) -> 64 channels of tap d
         hi = torch.empty_like(packed, dtype=torch.bfloat16)
         lo = torch.empty_like(packed, dtype=torch.bfloat16)
         L.check(lib.pips_split_bf16(L.ptr(packed), L.ptr(hi), L.ptr(lo), packed.numel(), _st()), "pips_split_bf16")
@@ -219,7 +219,7 @@ def adopt_filter(enc: Encoder, name: str, conv: torch.nn.Conv2d, hi: torch.Tenso
     w = conv.weight
     key = (w.data_ptr(), w._version)
     if conv is enc.conv1:
-        expect = (64, 7 * 64)
+        expect = (64, 4 * 64)
     else:
         cout, cin, R, S = w.shape
         bn = 64 if cout <= 64 else (128 if cout <= 128 else 256)
@@ -234,8 +234,8 @@ def adopt_filter(enc: Encoder, name: str, conv: torch.nn.Conv2d, hi: torch.Tenso
 
 def fnet_tc(enc: Encoder, rgb: torch.Tensor) -> torch.Tensor:
     """rgb (N,3,H,W) fp32 or bf16 with values 0..255 (NOT normalised) -> feature maps (N,H/stride,W/stride,128) NHWC.
-    The whole encoder on libpips_b200: the 7x7/2 stem as a 7x1 tcgen05 convolution over the column-unfolded,
-    normalised image (pips_stem_pack), residual stages and head on pips_conv_tc, element-wise stages fused."""
+    The whole encoder on libpips_b200: the 7x7/2 stem as a 4x1 stride-1 tcgen05 convolution over the unfolded,
+    normalised image (pips_stem_pack: row pairs x 7 column taps x 3 colours per pixel), residual stages and head on pips_conv_tc, element-wise stages fused."""
     assert rgb.is_cuda and rgb.dtype in (torch.float32, torch.bfloat16)
     lib = L.load()
     LAUNCHES[0] = 0
@@ -245,14 +245,13 @@ def fnet_tc(enc: Encoder, rgb: torch.Tensor) -> torch.Tensor:
     H8, W8 = H // enc.stride, W // enc.stride
     x = rgb
 
-    Wo = (W - 1) // 2 + 1
-    unf = _Pair(N, H, Wo, 64, rgb.device)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    unf = _Pair(N, Ho + 3, Wo, 64, rgb.device)                   # row pairs (2j-3, 2j-2) x 7 column taps x 3 colours
     L.check(lib.pips_stem_pack(L.ptr(rgb), 0 if rgb.dtype == torch.float32 else 1, N, H, W, L.ptr(unf.hi), L.ptr(unf.lo), _st()),
             "pips_stem_pack")
     w_hi, w_lo = _packed_stem_weight(enc.conv1)
-    Ho = (H - 1) // 2 + 1
     y = torch.empty(N, Ho, Wo, 64, dtype=torch.float32, device=rgb.device)
-    L.check(lib.pips_conv_tc_aniso(L.ptr(unf.hi), L.ptr(unf.lo), N, H, Wo, 64, L.ptr(w_hi), L.ptr(w_lo), 64, 7, 1, 2, 1, 3, 0,
+    L.check(lib.pips_conv_tc_aniso(L.ptr(unf.hi), L.ptr(unf.lo), N, Ho + 3, Wo, 64, L.ptr(w_hi), L.ptr(w_lo), 64, 4, 1, 1, 1, 0, 0,
                                    None, L.ptr(y), _st()), "pips_conv_tc_aniso")
     LAUNCHES[0] += 2                                   # stem_pack + stem conv
     X, XP = _apply_pair(ops, y, ops.stats(y), relu_main=True, plain=True)

@@ -19,7 +19,7 @@ python - <<PY
 import json
 d=json.load(open("gpurun_out/${tag}_bench.json"))
 print("ms/step", d["ms_per_step"], "e2e", d["e2e"]["ms_per_step"], "clk", d["clocks"]["sm_mhz"])
-print(d["kernel_ms_per_iteration"], d["loop_only"])
+print(d["kernel_ms_per_iteration"], d["loop_only"], "fnet", d.get("fnet_ms"))
 for k in ("n4096_1gpu","cfg1_demo_shape_1gpu","cfg4_1gpu"):
     print(k, d.get(k,{}).get("ms_per_step"), d.get(k,{}).get("error"))
 print(d.get("cfg5_chain_1gpu"))

@@ -139,3 +139,19 @@ def test_plain_c_consumer_links_and_struct_layouts_match(tmp_path):
     assert int(sizes["pips_weights"]) == ctypes.sizeof(L.Weights)
     assert int(sizes["pips_workspace"]) == ctypes.sizeof(L.Workspace)
     assert int(sizes["pips_problem"]) == ctypes.sizeof(L.Problem)
+
+
+def test_zero_edit_shim_serves_nets_pips():
+    """shim/ before the reference on sys.path: `from nets.pips import Pips` (demo.py:9) is pips_b200.Pips, other modules
+    of the reference's `nets` package still resolve to the reference checkout (when it is present)."""
+    import subprocess
+    import sys
+    ref = "/root/reference"
+    code = ("import sys; from nets.pips import Pips; import pips_b200; assert Pips is pips_b200.Pips; "
+            "m = Pips(S=8, stride=4); assert len(m.state_dict()) == 200; print('shim ok')")
+    if os.path.isdir(ref):
+        code += "; import nets.raft_core.util as u; assert u.__file__.startswith('/root/reference'); print('reference nets.* still visible')"
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "shim"), ROOT] + ([ref] if os.path.isdir(ref) else [])))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "shim ok" in out.stdout

@@ -177,6 +177,17 @@ int pips_resize_pair(const float* src, int N, int Hs, int Ws, int C, void* dst_h
 int pips_conv_tc(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp, const void* w_hi, const void* w_lo,
                  int Cout, int R, int S, int stride, int pad, const float* bias, float* out, void* stream);
 
+/* 3x3 / stride 1 / pad 1 convolution with 64 input and 64 output channels (BasicEncoder layer1, nets/pips.py:135-136):
+ * every input row is loaded once into a ring of row buffers and serves all 9 filter taps (csrc/conv_rows.cu).
+ * x_hi/x_lo (N,H,W,64) bf16, w_hi/w_lo (64, 9*64) bf16 [k = (r*3+s)*64 + ci], out (N,H,W,64) fp32.  partial (optional):
+ * (N, pips_conv_rows_chunks(H,W), 2, 64) per-chunk (sum, sum of squares) of `out` per channel -- the InstanceNorm
+ * statistics (nets/pips.py:154-157), reduced by pips_inorm_finalize. */
+int pips_conv_rows_chunks(int H, int W);
+int pips_conv_rows(const void* x_hi, const void* x_lo, int N, int H, int W, const void* w_hi, const void* w_lo, float* out,
+                   float* partial, void* stream);
+/* (mean, 1/sqrt(var + 1e-5)) per (image, channel) from `chunks` partial (sum, sum of squares) rows per image. */
+int pips_inorm_finalize(const float* partial, int N, int chunks, int HW, int C, float* stats, void* stream);
+
 int pips_conv_tc_aniso(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp, const void* w_hi, const void* w_lo,
                        int Cout, int R, int S, int stride_y, int stride_x, int pad_y, int pad_x, const float* bias, float* out,
                        void* stream);

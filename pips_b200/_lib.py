@@ -95,6 +95,9 @@ _SIGNATURES = {
     "pips_conv_tc": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "pips_conv_tc_aniso": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "pips_stem_pack": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "pips_conv_rows_chunks": (_i, [_i, _i]),
+    "pips_conv_rows": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "pips_inorm_finalize": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "pips_mixer_forward": (_i, [C.POINTER(Weights), C.POINTER(Workspace), _i, _i, _p]),
     "pips_refine_iter": (_i, [C.POINTER(Problem), C.POINTER(Weights), C.POINTER(Workspace), _p, _p]),
 }

@@ -252,6 +252,15 @@ extern "C" int pips_inorm_stats(const float* y, int N, int HW, int C, float* par
     return e == cudaSuccess ? 0 : fail_cuda("pips_inorm_stats: finalize", e);
 }
 
+// statistics from per-chunk partials some other kernel produced (pips_conv_rows accumulates them in its epilogue)
+extern "C" int pips_inorm_finalize(const float* partial, int N, int chunks, int HW, int C, float* stats, void* stream) {
+    if (!partial || !stats) return fail("pips_inorm_finalize: null pointer");
+    if (N <= 0 || HW <= 0 || C <= 0 || chunks <= 0) return fail("pips_inorm_finalize: bad shape");
+    cudaError_t e = launch_pdl(inorm_finalize_kernel, dim3(N), dim3(256), 0, static_cast<cudaStream_t>(stream), partial, chunks, HW, C, stats);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail_cuda("pips_inorm_finalize", e);
+}
+
 static int inorm_apply_impl(const float* y, const float* stats_y, const float* r, const float* stats_r, int relu_main, int relu_out,
                             float* out_plain, float* out_split, int split_ld, void* out_hi, void* out_lo, int pair_ld, int N, int HW,
                             int C, void* stream) {

@@ -11,6 +11,8 @@ Reference semantics: BasicEncoder.forward nets/pips.py:247-281, ResidualBlock.fo
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -173,6 +175,38 @@ def conv_tc(x: _Pair, conv: torch.nn.Conv2d, bias: bool = False) -> torch.Tensor
     return out
 
 
+def conv_rows_ok(x: _Pair, conv: torch.nn.Conv2d) -> bool:
+    """The row-ring kernel (csrc/conv_rows.cu) covers BasicEncoder's layer1 convolutions: 3x3, stride 1, pad 1, 64 -> 64."""
+    return (x.C == 64 and x.Cp == 64 and tuple(conv.weight.shape) == (64, 64, 3, 3) and conv.stride == (1, 1)
+            and conv.padding == (1, 1) and os.environ.get("PIPS_B200_CONV_ROWS", "1") != "0")
+
+
+def conv_rows(x: _Pair, conv: torch.nn.Conv2d):
+    """-> (out (N,H,W,64) fp32, InstanceNorm statistics (N,2,64) of out): the statistics come from partial sums the
+    convolution's epilogue accumulates, so no separate pass reads the output."""
+    lib = L.load()
+    N, H, W = x.shape
+    w_hi, w_lo = _packed_weight(conv)
+    dev = x.hi.device
+    out = torch.empty(N, H, W, 64, dtype=torch.float32, device=dev)
+    chunks = lib.pips_conv_rows_chunks(H, W)
+    partial = torch.empty(N, chunks, 2, 64, dtype=torch.float32, device=dev)
+    st = torch.empty(N, 2, 64, dtype=torch.float32, device=dev)
+    L.check(lib.pips_conv_rows(L.ptr(x.hi), L.ptr(x.lo), N, H, W, L.ptr(w_hi), L.ptr(w_lo), L.ptr(out), L.ptr(partial), _st()),
+            "pips_conv_rows")
+    L.check(lib.pips_inorm_finalize(L.ptr(partial), N, chunks, H * W, 64, L.ptr(st), _st()), "pips_inorm_finalize")
+    LAUNCHES[0] += 2
+    return out, st
+
+
+def _conv_stats(ops: _Ops, x: _Pair, conv: torch.nn.Conv2d):
+    """Convolution feeding an InstanceNorm: (output, statistics)."""
+    if conv_rows_ok(x, conv):
+        return conv_rows(x, conv)
+    y = conv_tc(x, conv)
+    return y, ops.stats(y)
+
+
 def _apply_pair(ops: _Ops, y, stats, r=None, stats_r=None, relu_main=True, relu_out=False, plain=False):
     N, H, W, C = y.shape
     out_p = torch.empty_like(y) if plain else None
@@ -261,10 +295,9 @@ def fnet_tc(enc: Encoder, rgb: torch.Tensor) -> torch.Tensor:
     c_off = 0
     for i in range(1, 5):
         for blk in getattr(enc, f"layer{i}"):
-            y1 = conv_tc(XP, blk.conv1)
-            _, AP = _apply_pair(ops, y1, ops.stats(y1), relu_main=True)
-            y2 = conv_tc(AP, blk.conv2)
-            s2 = ops.stats(y2)
+            y1, s1 = _conv_stats(ops, XP, blk.conv1)
+            _, AP = _apply_pair(ops, y1, s1, relu_main=True)
+            y2, s2 = _conv_stats(ops, AP, blk.conv2)
             if blk.downsample is not None:
                 d = conv_tc(XP, blk.downsample[0])
                 X, XP = _apply_pair(ops, y2, s2, r=d, stats_r=ops.stats(d), relu_main=True, relu_out=True, plain=True)

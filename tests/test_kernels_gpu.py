@@ -376,3 +376,35 @@ def test_conv_tc(N, H, W, cin, cout, k, stride, pad, bias):
     scale = ref.abs().max().item()
     print(f"conv_tc {cin}->{cout} k{k} s{stride}: max err {err:.2e} (|out| max {scale:.2f})")
     assert err < 3e-4 * max(1.0, scale)
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 24, 40), (1, 45, 300), (3, 7, 130), (2, 192, 256), (1, 90, 160)])
+def test_conv_rows(N, H, W):
+    """The row-ring 3x3 convolution of layer1 (csrc/conv_rows.cu; nets/pips.py:135-136, :154-157): output against an
+    fp64 convolution, the InstanceNorm statistics from its epilogue against the statistics of its own output, and the
+    generic tap-by-tap kernel (conv_tc.cu) on the same operands.  Widths below / across the 256-pixel pair block,
+    heights that are no multiple of the 8-row work item."""
+    from pips_b200.encoder_fast import _Pair, conv_rows, conv_rows_ok, conv_tc
+    torch.manual_seed(23)
+    conv = torch.nn.Conv2d(64, 64, 3, stride=1, padding=1).to(DEV)
+    x = torch.randn(N, H, W, 64, device=DEV)
+    pair = _Pair(N, H, W, 64, DEV)
+    hi = x.to(torch.bfloat16)
+    pair.hi.copy_(hi)
+    pair.lo.copy_((x - hi.float()).to(torch.bfloat16))
+    assert conv_rows_ok(pair, conv)
+    out, st = conv_rows(pair, conv)
+    gen = conv_tc(pair, conv)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), conv.weight.double(), None, stride=1, padding=1).permute(0, 2, 3, 1)
+    err = (out.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    mean = out.double().mean(dim=(1, 2))
+    rstd = 1.0 / torch.sqrt(out.double().var(dim=(1, 2), unbiased=False) + 1e-5)
+    e_mean = (st[:, 0].double() - mean).abs().max().item()
+    e_rstd = ((st[:, 1].double() - rstd) / rstd).abs().max().item()
+    print(f"conv_rows {N}x{H}x{W}: max err {err:.2e} (|out| max {scale:.2f}); vs conv_tc {float((out - gen).abs().max()):.2e}; "
+          f"stats: mean err {e_mean:.2e}, rstd rel err {e_rstd:.2e}")
+    assert err < 3e-4 * max(1.0, scale)
+    assert (out - gen).abs().max().item() < 1e-4 * max(1.0, scale)     # same products, same K order: fp32 accumulation noise only
+    assert e_mean < 1e-5 and e_rstd < 1e-5

@@ -8,31 +8,37 @@
 //     image by TMA) live in a 4-slot ring of row buffers; moving to the next output row loads ONE new row (33 KB for the
 //     (hi, lo) pair) -- 8.7x less operand traffic than 9 boxes per tile;
 //   * filter tap (dr, ds) is the 128 contiguous 128-byte pixels starting at pixel ds of ring row y+dr: an UMMA
-//     descriptor whose start address is offset by ds pixels (SWIZZLE_128B `base offset` = address bits 7..9);
+//     descriptor whose start address is offset by ds pixels (the swizzle follows absolute address bits: base offset 0);
 //   * all 9 taps' weights (72 KB per CTA) are loaded once per CTA and stay resident;
 //   * a CTA pair (cta_group::2, M = 256) covers 256 pixels of the row; the accumulator is 64 TMEM columns, 4 in flight;
 //   * InstanceNorm statistics (nets/pips.py:154-157) are accumulated in the epilogue: per work item (image, 256-pixel
 //     column block, 8 rows) and CTA one partial (sum, sum of squares) per channel -- the layout pips_inorm_finalize
 //     reduces in fp64, deterministic and independent of the batch size; the separate statistics pass over the 400 MB
 //     layer-1 activations disappears.
-// Same bf16x3 arithmetic (hi*hi + lo*hi + hi*lo, fp32 accumulation) and the same K order (tap-major, then channel) as
-// conv_tc.cu.
+//   * two MMAs per K step instead of three: these N = 64 MMAs are dispatch-bound (ncu: tensor pipe 45 % active at ~70 clk
+//     per instruction against 32 clk of math), so the hi*hi and hi*lo terms share ONE instruction with N = 128 --
+//     B = [w_hi ; w_lo], rank 0's shared memory holding the w_hi rows and rank 1's the w_lo rows -- into two 64-column
+//     partial accumulators, and lo*hi is a second instruction (N = 64) into the first; the epilogue adds the two partials.
+// Same bf16x3 products (hi*hi + lo*hi + hi*lo, fp32 accumulation) and K order (tap-major, then channel) as conv_tc.cu.
 #include "gemm_common.cuh"
 
 namespace pips {
 
 constexpr int R_THREADS = 384;                       // warp 0 TMA, 1 MMA, 2 TMEM, 3 idle, 4..11 epilogue
 constexpr int R_ROWS_PER_ITEM = 8;
-constexpr int R_RING = 4;
+constexpr int R_RING = 3;
 constexpr int R_BOX_PX = 130;                        // 128 output pixels + 1 halo pixel on each side
 constexpr uint32_t R_ROW_TX = R_BOX_PX * 128;        // bytes TMA writes per row and operand half (hi or lo)
 constexpr uint32_t R_ROW_BYTES = 17 * 1024;          // slot stride (1 KB aligned: SWIZZLE_128B pattern repeats every 1 KB)
-constexpr uint32_t R_W_TAP = 32 * 128;               // this CTA's 32 filter rows x 64 channels of one tap, one half
-constexpr uint32_t R_OFF_W = R_RING * 2 * R_ROW_BYTES;            // 136 KB
-constexpr uint32_t R_OFF_COMB = R_OFF_W + 9 * 2 * R_W_TAP;        // +72 KB
+// Filter operands per tap and CTA (see "two MMAs per K step" below): [main: 64 rows x 128 B | second: 32 rows x 128 B]
+//   main    rank 0: w_hi rows 0..63     rank 1: w_lo rows 0..63      -> B of the N = 128 MMA  a_hi . [w_hi ; w_lo]
+//   second  rank 0: w_hi rows 0..31     rank 1: w_hi rows 32..63     -> B of the N = 64 MMA   a_lo . w_hi
+constexpr uint32_t R_W_MAIN = 64 * 128, R_W_SECOND = 32 * 128, R_W_TAP = R_W_MAIN + R_W_SECOND;   // 12 KB
+constexpr uint32_t R_OFF_W = R_RING * 2 * R_ROW_BYTES;            // 102 KB
+constexpr uint32_t R_OFF_COMB = R_OFF_W + 9 * R_W_TAP;            // +108 KB
 constexpr uint32_t R_OFF_BARS = R_OFF_COMB + 8 * 64 * 4;          // 8 epilogue warps x (32 sums + 32 sums of squares)
 constexpr uint32_t R_SMEM_BYTES = R_OFF_BARS + 256 + 1024;
-constexpr int R_ACC = 4;                             // accumulator stages of 64 TMEM columns
+constexpr int R_ACC = 4;                             // accumulator stages of 128 TMEM columns (two partial sums, see below)
 
 struct RowsArgs {
     int N, H, W;
@@ -41,11 +47,6 @@ struct RowsArgs {
     float* out;                 // (N, H, W, 64) fp32
     float* partial;             // optional (N, px_blocks * row_chunks * 2, 2, 64)
 };
-
-// SWIZZLE_128B K-major descriptor whose start address may sit on any 128-byte row of the swizzle pattern
-__device__ __forceinline__ uint64_t umma_desc_sw128_row(uint32_t smem_addr) {
-    return umma_desc_sw128(smem_addr) | (static_cast<uint64_t>((smem_addr >> 7) & 7) << 49);
-}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R_THREADS, 1)
 conv_rows_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -87,7 +88,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc_pair(smem_u32(tmem_slot), R_ACC * 64);
+        tmem_alloc_pair(smem_u32(tmem_slot), R_ACC * 128);
         tmem_relinquish_pair();
     }
     tc_fence_before();
@@ -103,11 +104,13 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             if (lane == 0) {
                 // the filter is a constant of the forward: loaded before the dependency wait
                 const uint32_t wb = leader_addr(wfull);
-                if (leader) mbar_arrive_expect_tx(wfull, 2 * 9 * 2 * R_W_TAP);
+                if (leader) mbar_arrive_expect_tx(wfull, 2 * 9 * R_W_TAP);
                 else mbar_arrive_cluster(wfull, 0);
+                const CUtensorMap* main_map = leader ? &map_w_hi : &map_w_lo;
                 for (int tap = 0; tap < 9; ++tap) {
-                    tma_load_2d_pair(wsm0 + tap * 2 * R_W_TAP, &map_w_hi, wb, tap * 64, static_cast<int>(rank) * 32);
-                    tma_load_2d_pair(wsm0 + tap * 2 * R_W_TAP + R_W_TAP, &map_w_lo, wb, tap * 64, static_cast<int>(rank) * 32);
+                    tma_load_2d_pair(wsm0 + tap * R_W_TAP, main_map, wb, tap * 64, 0);
+                    tma_load_2d_pair(wsm0 + tap * R_W_TAP + R_W_SECOND, main_map, wb, tap * 64, 32);
+                    tma_load_2d_pair(wsm0 + tap * R_W_TAP + R_W_MAIN, &map_w_hi, wb, tap * 64, static_cast<int>(rank) * 32);
                 }
                 pdl_wait();                                   // the activation comes from the previous kernel
                 uint32_t ld = 0;                              // rows loaded so far: slot = ld % R_RING
@@ -130,8 +133,13 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
             __syncwarp();
         } else if (warp == 1) {
             // ------------------------------------------------------------ MMA issuer (leader only)
-            if (leader && lane == 0) {
-                constexpr uint32_t idesc = umma_idesc_bf16(256, 64);
+            // The whole warp runs this loop (warp-uniform control flow and values, so descriptors live in uniform
+            // registers); one elected lane issues.  With `if (lane == 0)` around the loop the compiler moved every operand
+            // of every MMA from vector to uniform registers under an election loop -- 14 instructions per MMA, which for
+            // these short N = 64 MMAs (108 per tile) made instruction issue, not the tensor pipe, the limit.
+            if (leader) {
+                constexpr uint32_t idesc_wide = umma_idesc_bf16(256, 128), idesc_narrow = umma_idesc_bf16(256, 64);
+                const bool elected = elect_one();
                 mbar_wait(wfull, 0);
                 uint32_t base_ld = 0, waited = 0;             // first ring index of the item; rows already waited for
                 int it = 0;
@@ -140,38 +148,51 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                     const int y0 = (rem % a.row_chunks) * R_ROWS_PER_ITEM;
                     const int ntiles = min(a.H, y0 + R_ROWS_PER_ITEM) - y0;
                     for (int j = 0; j < ntiles; ++j, ++it) {
-                        while (waited <= base_ld + j + 2) {    // rows arrive in order; tile j needs ring indices base+j .. base+j+2
-                            mbar_wait(rfull0 + 8 * (waited % R_RING), (waited / R_RING) & 1);
-                            ++waited;
-                        }
                         const uint32_t as = it % R_ACC, aphase = (it / R_ACC) & 1;
                         mbar_wait(tempty0 + 8 * as, aphase ^ 1);
                         tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + as * 64;
-#pragma unroll 1
+                        const uint32_t d_tmem = tmem_base + as * 128;
+#pragma unroll
                         for (int dr = 0; dr < 3; ++dr) {
+                            // rows arrive in order; the taps of filter row dr need ring index base + j + dr.  Waiting per filter
+                            // row (not for all three rows up front) and releasing a row right after its last use (below) lets a
+                            // 3-slot ring suffice: the load of the next row has 1.3 tile times before the tensor pipe needs it.
+                            while (waited <= base_ld + j + dr) {
+                                mbar_wait(rfull0 + 8 * (waited % R_RING), (waited / R_RING) & 1);
+                                ++waited;
+                            }
+                            tc_fence_after();
                             const uint32_t row = ring0 + ((base_ld + j + dr) % R_RING) * 2 * R_ROW_BYTES;
 #pragma unroll
                             for (int ds = 0; ds < 3; ++ds) {
-                                const uint32_t wt = wsm0 + (dr * 3 + ds) * 2 * R_W_TAP;
-                                const uint64_t a_hi = umma_desc_sw128_row(row + ds * 128);
-                                const uint64_t a_lo = umma_desc_sw128_row(row + R_ROW_BYTES + ds * 128);
-                                const uint64_t w_hi = umma_desc_sw128(wt), w_lo = umma_desc_sw128(wt + R_W_TAP);
+                                const uint32_t wt = wsm0 + (dr * 3 + ds) * R_W_TAP;
+                                // start address on pixel ds of the row buffer: the tensor core applies the 128-byte swizzle to
+                                // ABSOLUTE shared-memory address bits (as TMA did when it wrote the row), so a start that is a
+                                // whole number of 128-byte rows into the 1 KB pattern needs nothing else -- descriptor base
+                                // offset 0.  (Measured: with base offset = (addr >> 7) & 7 every ds != 0 tap is wrong.)
+                                const uint64_t a_hi = umma_desc_sw128(row + ds * 128);
+                                const uint64_t a_lo = umma_desc_sw128(row + R_ROW_BYTES + ds * 128);
+                                const uint64_t w_main = umma_desc_sw128(wt), w_second = umma_desc_sw128(wt + R_W_MAIN);
 #pragma unroll
                                 for (int k = 0; k < BK / UMMA_K; ++k) {
                                     const uint64_t adv = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
-                                    umma_f16_pair(d_tmem, a_hi + adv, w_hi + adv, idesc, (dr | ds | k) != 0);
-                                    umma_f16_pair(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
-                                    umma_f16_pair(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                                    if (elected) {
+                                        umma_f16_pair(d_tmem, a_hi + adv, w_main + adv, idesc_wide, (dr | ds | k) != 0);   // hi*hi | hi*lo
+                                        umma_f16_pair(d_tmem, a_lo + adv, w_second + adv, idesc_narrow, 1);                // + lo*hi
+                                    }
                                 }
                             }
+                            // ring row base + j (input row y-1) had its last use in the dr = 0 taps of this tile
+                            if (dr == 0 && elected) umma_commit_pair(rempty0 + 8 * ((base_ld + j) % R_RING));
                         }
-                        umma_commit_pair(tfull0 + 8 * as);
-                        umma_commit_pair(rempty0 + 8 * ((base_ld + j) % R_RING));           // row y-1 is not needed again
-                        if (j == ntiles - 1) {                                                 // nor are the item's last two rows
-                            umma_commit_pair(rempty0 + 8 * ((base_ld + j + 1) % R_RING));
-                            umma_commit_pair(rempty0 + 8 * ((base_ld + j + 2) % R_RING));
+                        if (elected) {
+                            umma_commit_pair(tfull0 + 8 * as);
+                            if (j == ntiles - 1) {                                                 // the item's last two rows
+                                umma_commit_pair(rempty0 + 8 * ((base_ld + j + 1) % R_RING));
+                                umma_commit_pair(rempty0 + 8 * ((base_ld + j + 2) % R_RING));
+                            }
                         }
+                        __syncwarp();
                     }
                     base_ld += ntiles + 2;
                 }
@@ -197,9 +218,13 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
                 const uint32_t as = it % R_ACC, aphase = (it / R_ACC) & 1;
                 mbar_wait(tfull0 + 8 * as, aphase);
                 tc_fence_after();
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + as * 64 + half * 32 + (static_cast<uint32_t>(q * 32) << 16), v);
+                uint32_t v[32], v2[32];
+                const uint32_t tcol = tmem_base + as * 128 + half * 32 + (static_cast<uint32_t>(q * 32) << 16);
+                tmem_ld_32x32(tcol, v);                       // hi*hi + lo*hi
+                tmem_ld_32x32(tcol + 64, v2);                 // hi*lo
                 tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(__uint_as_float(v[c]) + __uint_as_float(v2[c]));
                 tc_fence_before();
                 mbar_arrive_cluster(tempty0 + 8 * as, 0);     // values are in registers: the accumulator can be reused
                 if (ok) {
@@ -247,7 +272,7 @@ conv_rows_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_cons
 
     tc_fence_before();
     cluster_sync_all();
-    if (warp == 2) tmem_dealloc_pair(tmem_base, R_ACC * 64);
+    if (warp == 2) tmem_dealloc_pair(tmem_base, R_ACC * 128);
 }
 
 }  // namespace pips
@@ -268,6 +293,7 @@ extern "C" int pips_conv_rows(const void* x_hi, const void* x_lo, int N, int H, 
     RowsArgs a;
     a.N = N; a.H = H; a.W = W; a.px_blocks = (W + 255) / 256; a.row_chunks = (H + R_ROWS_PER_ITEM - 1) / R_ROWS_PER_ITEM;
     a.out = out; a.partial = partial;
+
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     {
         cuuint64_t gdim[4] = {64, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N)};

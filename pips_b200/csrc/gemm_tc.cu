@@ -126,7 +126,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // whole warp, warp-uniform control flow (descriptors stay in uniform registers); one elected lane issues
+        {
+            const bool elected = elect_one();
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
             uint32_t stage = 0, phase = 0;
             int it = 0;
@@ -146,14 +148,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t adv = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);   // 32 B per K=16 step
-                        umma_f16(d_tmem, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+                        if (elected) umma_f16(d_tmem, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
                         if (TERMS == 3) {
-                            umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
-                            umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                            if (elected) umma_f16(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
+                            if (elected) umma_f16(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
                         }
                     }
-                    umma_commit(empty0 + 8 * stage);          // smem slot reusable once these MMAs retire
-                    if (kb == num_kb - 1) umma_commit(tfull0 + 8 * as);
+                    if (elected) umma_commit(empty0 + 8 * stage);          // smem slot reusable once these MMAs retire
+                    if (elected && kb == num_kb - 1) umma_commit(tfull0 + 8 * as);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }

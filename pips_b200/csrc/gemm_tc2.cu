@@ -153,7 +153,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         __syncwarp();
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (leader only)
-        if (leader && lane == 0) {
+        // whole warp, warp-uniform control flow (descriptors stay in uniform registers); one elected lane issues
+        if (leader) {
+            const bool elected = elect_one();
             constexpr uint32_t idesc_wide = umma_idesc_bf16(P_BM, P_BN);
             constexpr uint32_t idesc_narrow = umma_idesc_bf16(P_BM, P_BN / 2);
             uint32_t stage = 0, phase = 0;
@@ -176,14 +178,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t adv = static_cast<uint64_t>((k * UMMA_K * 2) >> 4);
-                        umma_f16_pair(d_tmem, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+                        if (elected) umma_f16_pair(d_tmem, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
                         if (TERMS == 3) {
-                            umma_f16_pair(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
-                            umma_f16_pair(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
+                            if (elected) umma_f16_pair(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
+                            if (elected) umma_f16_pair(d_tmem, a_hi + adv, w_lo + adv, idesc, 1);
                         }
                     }
-                    umma_commit_pair(empty0 + 8 * stage);
-                    if (kb == num_kb - 1) umma_commit_pair(tfull0 + 8 * as);
+                    if (elected) umma_commit_pair(empty0 + 8 * stage);
+                    if (elected && kb == num_kb - 1) umma_commit_pair(tfull0 + 8 * as);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }

@@ -177,8 +177,12 @@ def conv_tc(x: _Pair, conv: torch.nn.Conv2d, bias: bool = False) -> torch.Tensor
 
 def conv_rows_ok(x: _Pair, conv: torch.nn.Conv2d) -> bool:
     """The row-ring kernel (csrc/conv_rows.cu) covers BasicEncoder's layer1 convolutions: 3x3, stride 1, pad 1, 64 -> 64."""
+    W = x.shape[2]
+    # a CTA pair covers 256 pixels of a row: widths that fill less than 3/4 of the last pair (e.g. 320 = 256 + 64) are
+    # faster on the tap-by-tap kernel (measured: 8 x 180 x 320 maps, 136 vs 121 + 25 us)
+    fill = W / float(((W + 255) // 256) * 256)
     return (x.C == 64 and x.Cp == 64 and tuple(conv.weight.shape) == (64, 64, 3, 3) and conv.stride == (1, 1)
-            and conv.padding == (1, 1) and os.environ.get("PIPS_B200_CONV_ROWS", "1") != "0")
+            and conv.padding == (1, 1) and fill >= 0.75 and os.environ.get("PIPS_B200_CONV_ROWS", "1") != "0")
 
 
 def conv_rows(x: _Pair, conv: torch.nn.Conv2d):

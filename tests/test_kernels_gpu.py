@@ -378,7 +378,7 @@ def test_conv_tc(N, H, W, cin, cout, k, stride, pad, bias):
     assert err < 3e-4 * max(1.0, scale)
 
 
-@pytest.mark.parametrize("N,H,W", [(2, 24, 40), (1, 45, 300), (3, 7, 130), (2, 192, 256), (1, 90, 160)])
+@pytest.mark.parametrize("N,H,W", [(2, 24, 40), (1, 45, 300), (3, 7, 130), (2, 192, 256), (1, 90, 160), (1, 33, 640)])
 def test_conv_rows(N, H, W):
     """The row-ring 3x3 convolution of layer1 (csrc/conv_rows.cu; nets/pips.py:135-136, :154-157): output against an
     fp64 convolution, the InstanceNorm statistics from its epilogue against the statistics of its own output, and the
@@ -392,7 +392,7 @@ def test_conv_rows(N, H, W):
     hi = x.to(torch.bfloat16)
     pair.hi.copy_(hi)
     pair.lo.copy_((x - hi.float()).to(torch.bfloat16))
-    assert conv_rows_ok(pair, conv)
+    assert conv_rows_ok(pair, conv) == (W / (((W + 255) // 256) * 256) >= 0.75)      # narrow last pair blocks use conv_tc in the encoder
     out, st = conv_rows(pair, conv)
     gen = conv_tc(pair, conv)
     torch.cuda.synchronize()

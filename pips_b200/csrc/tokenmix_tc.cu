@@ -137,6 +137,13 @@ __device__ __forceinline__ void layernorm8_fast(const float (&x)[8][4], float (&
     }
 }
 
+// elect.sync needs the whole warp converged: called at a point where all 128 threads arrive, evaluated in warp 0 only
+__device__ __forceinline__ bool elect_one_in_warp0(int warp) {
+    bool e = false;
+    if (warp == 0) e = elect_one();
+    return e;
+}
+
 __global__ void __launch_bounds__(TT_THREADS, TT_CTAS_PER_SM)
 tokenmix_tc_kernel(float* __restrict__ x, int seqs, const float* __restrict__ ln1_w, const float* __restrict__ ln1_b,
                    const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
@@ -194,10 +201,11 @@ tokenmix_tc_kernel(float* __restrict__ x, int seqs, const float* __restrict__ ln
     constexpr uint32_t idesc1 = umma_idesc_bf16(128, 32);
     constexpr uint32_t idesc2 = umma_idesc_bf16(128, 16);
     const uint64_t d_b1a = umma_desc_nosw(sbase + TT_OFF_B1A, 128, 256), d_b1b = umma_desc_nosw(sbase + TT_OFF_B1B, 128, 256);
+    const bool elected = warp == 0 && elect_one_in_warp0(warp);   // the lane of warp 0 that issues the MMAs
 
     pdl_wait();                                             // x is written by the previous kernel (weights above are constants)
     // x of the track after the current one is fetched into registers while the current track's GELU phase runs; the
-    // current x is dropped after LayerNorm 1 and re-read (an L2 hit) for the residual, so that both fit 128 registers
+    // current x is dropped after LayerNorm 1 and parked in shared memory for the residual, so that both fit 128 registers
     float4 nx[8];
     if (static_cast<int>(blockIdx.x) < seqs) {
         const float* src = x + static_cast<size_t>(blockIdx.x) * 8 * 512 + t * 4;
@@ -234,15 +242,17 @@ tokenmix_tc_kernel(float* __restrict__ x, int seqs, const float* __restrict__ ln
         fence_proxy_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (t == 0) {
+        if (warp == 0) {                                     // warp-uniform: descriptors in uniform registers, one lane issues
             tc_fence_after();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const uint64_t a = umma_desc_nosw(sbase + TT_OFF_A1 + i * TT_A1_TILE, 128, 256);
-                umma_f16(tmem_base + i * 32, a, d_b1a, idesc1, 0);
-                umma_f16(tmem_base + i * 32, a, d_b1b, idesc1, 1);
+                if (elected) {
+                    umma_f16(tmem_base + i * 32, a, d_b1a, idesc1, 0);
+                    umma_f16(tmem_base + i * 32, a, d_b1b, idesc1, 1);
+                }
             }
-            umma_commit(bar_h);
+            if (elected) umma_commit(bar_h);
         }
         if (seq + static_cast<int>(gridDim.x) < seqs) {      // next track's x: in flight during the GELU phase
             const float* src = x + static_cast<size_t>(seq + gridDim.x) * 8 * 512 + t * 4;
@@ -251,6 +261,16 @@ tokenmix_tc_kernel(float* __restrict__ x, int seqs, const float* __restrict__ ln
         }
         mbar_wait(bar_h, parity);
         tc_fence_after();
+        // GEMM1 is done with the A1 tiles: their 16 KB now take a copy of this track's x (cp.async, no registers held)
+        // for the residual at the end -- re-reading it from L2 there exposed ~500 cycles of latency per track
+        {
+            const uint32_t dst = sbase + TT_OFF_A1 + t * 16;
+            const float* src = x + base;
+#pragma unroll
+            for (int sr = 0; sr < 8; ++sr)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + sr * 2048), "l"(src + sr * 512) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
 
         // ---- per tile: GELU(H_i) -> G buffer (i & 1) -> GEMM2_i (Z_i lands on H_i's first 16 columns) while the
         // CUDA cores already work on H_{i+1}.  Each G-buffer barrier completes twice per track (parities 0, 1).
@@ -280,25 +300,30 @@ tokenmix_tc_kernel(float* __restrict__ x, int seqs, const float* __restrict__ ln
             fence_proxy_async_smem();
             tc_fence_before();                               // H_i fully read by this thread before Z_i may overwrite it
             __syncthreads();
-            if (t == 0) {
+            if (warp == 0) {
                 tc_fence_after();
                 const uint32_t d = tmem_base + i * 32;
                 const uint32_t ga = sbase + TT_OFF_G + (i & 1) * TT_G_TILE;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)                      // [g_hi | g_lo] . [w2_hi | w2_hi]
-                    umma_f16(d, umma_desc_nosw(ga + k * 256, 128, 1024), umma_desc_nosw(sbase + TT_OFF_B2A + k * 256, 128, 1024), idesc2, k != 0);
+                for (int k = 0; k < 4; ++k) {                    // [g_hi | g_lo] . [w2_hi | w2_hi]
+                    const uint64_t da = umma_desc_nosw(ga + k * 256, 128, 1024), db = umma_desc_nosw(sbase + TT_OFF_B2A + k * 256, 128, 1024);
+                    if (elected) umma_f16(d, da, db, idesc2, k != 0);
+                }
 #pragma unroll
-                for (int k = 0; k < 2; ++k)                      // g_hi . w2_lo
-                    umma_f16(d, umma_desc_nosw(ga + k * 256, 128, 1024), umma_desc_nosw(sbase + TT_OFF_B2B + k * 256, 128, 1024), idesc2, 1);
-                umma_commit(bar_g0 + 8 * (i & 1));
+                for (int k = 0; k < 2; ++k) {                    // g_hi . w2_lo
+                    const uint64_t da = umma_desc_nosw(ga + k * 256, 128, 1024), db = umma_desc_nosw(sbase + TT_OFF_B2B + k * 256, 128, 1024);
+                    if (elected) umma_f16(d, da, db, idesc2, 1);
+                }
+                if (elected) umma_commit(bar_g0 + 8 * (i & 1));
             }
         }
         // ---- residual, LN2, outputs
         float xv[8][4];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
-        for (int s = 0; s < 8; ++s) {                        // the residual input again (an L2 hit), under the last GEMM2s
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(x + base + s * 512));
-            xv[s][0] = v.x; xv[s][1] = v.y; xv[s][2] = v.z; xv[s][3] = v.w;
+        for (int sr = 0; sr < 8; ++sr) {                     // this thread's own copies: no CTA-wide barrier needed
+            const float4 v = *reinterpret_cast<const float4*>(smem + TT_OFF_A1 + sr * 2048 + t * 16);
+            xv[sr][0] = v.x; xv[sr][1] = v.y; xv[sr][2] = v.z; xv[sr][3] = v.w;
         }
         mbar_wait(bar_g0, 1);                                // GEMM2 of tiles 2 and 3 (and therefore of all) done
         mbar_wait(bar_g0 + 8, 1);

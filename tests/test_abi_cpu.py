@@ -18,7 +18,8 @@ def test_header_symbols_are_exported():
     lib = L.load()
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.pips_abi_version() == 2
+    macro = int(re.search(r"#define PIPS_B200_ABI_VERSION (\d+)", hdr).group(1))
+    assert lib.pips_abi_version() == macro == L.ABI_VERSION == 3
 
 
 def test_argument_validation_without_gpu():
@@ -27,6 +28,12 @@ def test_argument_validation_without_gpu():
     assert b"multiple of 64" in lib.pips_last_error()
     assert lib.pips_corr_gather(None, 0, 1, 7, 1, 16, 16, 0, 0, 0, None, 0, 0, 0, 0, 576, 0) != 0
     assert lib.pips_refine_iter(None, None, None, 0, 0) != 0
+    # round-2 entry points: the row-ring convolution and the statistics finalize
+    assert lib.pips_conv_rows(None, None, 1, 8, 8, None, None, None, None, None) != 0 and b"null pointer" in lib.pips_last_error()
+    assert lib.pips_conv_rows_chunks(192, 256) == 1 * 24 * 2 and lib.pips_conv_rows_chunks(180, 640) == 3 * 23 * 2
+    assert lib.pips_conv_rows_chunks(0, 5) == 0
+    assert lib.pips_inorm_finalize(None, 1, 1, 1, 64, None, None) != 0
+    assert lib.pips_stem_pack(None, 0, 1, 8, 8, None, None, None) != 0
 
 
 def test_state_dict_contract_matches_reference_spec():

@@ -275,6 +275,12 @@ def fnet_tc(enc: Encoder, rgb: torch.Tensor) -> torch.Tensor:
     The whole encoder on libpips_b200: the 7x7/2 stem as a 4x1 stride-1 tcgen05 convolution over the unfolded,
     normalised image (pips_stem_pack: row pairs x 7 column taps x 3 colours per pixel), residual stages and head on pips_conv_tc, element-wise stages fused."""
     assert rgb.is_cuda and rgb.dtype in (torch.float32, torch.bfloat16)
+    from .engine import nvtx_range
+    with nvtx_range("pips/fnet"):
+        return _fnet_tc(enc, rgb)
+
+
+def _fnet_tc(enc: Encoder, rgb: torch.Tensor) -> torch.Tensor:
     lib = L.load()
     LAUNCHES[0] = 0
     rgb = rgb.contiguous()

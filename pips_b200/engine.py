@@ -17,6 +17,24 @@ from . import _lib as L
 S_FRAMES = 8
 LATENT = 128
 
+# PIPS_B200_NVTX=1: NVTX ranges around the phases of a forward (encoder, pyramid + initial features, every refinement
+# iteration, visibility head) for `ncu --nvtx --nvtx-include "pips/iter3/"` and timeline tools.
+_NVTX = os.environ.get("PIPS_B200_NVTX", "0") == "1"
+
+
+class nvtx_range:
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
 
 def _round_up(v: int, m: int) -> int:
     return (v + m - 1) // m * m
@@ -264,7 +282,8 @@ class RefineEngine:
         st = self._stream()
         launches = 0
         if build_pyramid:
-            pyr.build(fmaps2d, st)
+            with nvtx_range("pips/pyramid"):
+                pyr.build(fmaps2d, st)
             launches += 4
         c0.copy_(c)
         if feat_init is None:
@@ -300,11 +319,13 @@ class RefineEngine:
                                          sel.numel(), L.ptr(scratch), L.ptr(fcps[0, 0, it]),
                                          fcps.stride(1), st), "pips_heatmap")
                 launches += 1 + (sel.numel() + 31) // 32
-            L.check(lib.pips_refine_iter(C.byref(prob), C.byref(wc), C.byref(ws.c), L.ptr(out[it]), st), "pips_refine_iter")
+            with nvtx_range(f"pips/iter{it}"):
+                L.check(lib.pips_refine_iter(C.byref(prob), C.byref(wc), C.byref(ws.c), L.ptr(out[it]), st), "pips_refine_iter")
             launches += 1 + (1 + 3 * L.DEPTH + 2) + 1
             if on_iter is not None:
                 on_iter(it, out[it])
-        L.check(lib.pips_vis_head(L.ptr(ffeats), wc.vis_w, wc.vis_b, L.ptr(vis), B, S, nc, st), "pips_vis_head")
+        with nvtx_range("pips/vis_head"):
+            L.check(lib.pips_vis_head(L.ptr(ffeats), wc.vis_w, wc.vis_b, L.ptr(vis), B, S, nc, st), "pips_vis_head")
         return launches + 1
 
     def refine(self, module, fmaps: torch.Tensor, coords: torch.Tensor, feat_init: Optional[torch.Tensor],

@@ -191,6 +191,13 @@ int pips_inorm_finalize(const float* partial, int N, int chunks, int HW, int C, 
 int pips_conv_tc_aniso(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp, const void* w_hi, const void* w_lo,
                        int Cout, int R, int S, int stride_y, int stride_x, int pad_y, int pad_x, const float* bias, float* out,
                        void* stream);
+/* pips_conv_tc_aniso that also accumulates, in its epilogue, the InstanceNorm partial statistics of its output
+ * (nets/pips.py:154-157): partial (N, pips_conv_tc_chunks(geometry), 2, Cout) fp32 per-chunk (sum, sum of squares) per
+ * channel; the chunking depends on the image geometry only.  Reduce with pips_inorm_finalize. */
+int pips_conv_tc_chunks(int H, int W, int R, int S, int stride_y, int stride_x, int pad_y, int pad_x);
+int pips_conv_tc_stats(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp, const void* w_hi, const void* w_lo,
+                       int Cout, int R, int S, int stride_y, int stride_x, int pad_y, int pad_x, const float* bias, float* out,
+                       float* partial, void* stream);
 /* nets/pips.py:436 + the unfolding of the 7x7/2 stem (:206) into a 4x1 stride-1 convolution: rgb (N,3,H,W) fp32
  * (dtype 0) or bf16 (dtype 1), 0..255 -> (N, Ho+3, Wo, 64) bf16 (hi, lo), Ho = (H-1)/2+1, Wo = (W-1)/2+1; pixel (j, ox)
  * holds input rows y = 2j-3 (channels 0..31) and y = 2j-2 (channels 32..63), channel k = s*3 + colour of a row =

@@ -95,6 +95,8 @@ _SIGNATURES = {
     "pips_conv_tc": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "pips_conv_tc_aniso": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "pips_stem_pack": (_i, [_p, _i, _i, _i, _i, _p, _p, _p]),
+    "pips_conv_tc_chunks": (_i, [_i] * 8),
+    "pips_conv_tc_stats": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "pips_conv_rows_chunks": (_i, [_i, _i]),
     "pips_conv_rows": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "pips_inorm_finalize": (_i, [_p, _i, _i, _i, _i, _p, _p]),

@@ -20,7 +20,8 @@ constexpr int C_THREADS = 384;
 constexpr uint32_t C_A_BYTES = 128 * BK * 2;          // 128 pixels x 64 channels bf16
 constexpr int C_MAX_STAGES = 8;
 constexpr uint32_t C_RING_BYTES = 192 * 1024;         // smem ring: stage = A_hi | A_lo | W_hi | W_lo, 2*(16 KB + BN/2*128 B)
-constexpr uint32_t C_SMEM_BYTES = C_RING_BYTES + 1024 + 256;
+constexpr uint32_t C_COMB_BYTES = 8 * 4 * 64 * 4;      // statistics exchange: 8 epilogue warps x up to 4 chunks x (32 sums + 32 squares)
+constexpr uint32_t C_SMEM_BYTES = C_RING_BYTES + C_COMB_BYTES + 1024 + 256;
 
 struct ConvArgs {
     int N, Ho, Wo, Cout;        // output (NHWC fp32, row stride Cout)
@@ -32,6 +33,13 @@ struct ConvArgs {
     int stages;                 // ring depth: 3 (BN = 256) .. 4 (BN = 64)
     const float* bias;          // [Cout] or null
     float* out;
+    // Work items: the tiles of ONE image in groups of G consecutive pair tiles (pt_img pair tiles per image, groups_img
+    // groups).  A group is the unit of the InstanceNorm partial statistics (nets/pips.py:154-157): with `partial` set, the
+    // epilogue accumulates (sum, sum of squares) per output channel over the group's valid pixels and every CTA writes one
+    // row partial[(img * groups_img + g) * 2 + rank][2][Cout] -- a layout fixed by the image geometry alone (never by the
+    // batch), reduced in fp64 by pips_inorm_finalize.
+    int G, groups_img, pt_img;
+    float* partial;             // optional
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C_THREADS, 1)
@@ -40,7 +48,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_RING_BYTES);
+    float* comb = reinterpret_cast<float*>(smem + C_RING_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C_RING_BYTES + C_COMB_BYTES);
     const uint32_t full0 = smem_u32(bars);
     const uint32_t empty0 = full0 + 8 * C_MAX_STAGES;
     const uint32_t tfull0 = empty0 + 8 * C_MAX_STAGES;
@@ -54,8 +63,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
     const int tiles_img = a.tiles_x * a.tiles_y;
-    const int total_tiles = a.N * tiles_img;
-    const int pair_tiles = (total_tiles + 1) >> 1;
+    const int num_items = a.N * a.groups_img;
     const int chunks = a.Cp / BK;
     const int num_kb = a.R * a.S * chunks;
     const uint32_t w_bytes = static_cast<uint32_t>(a.BN / 2) * BK * 2;       // this CTA's half of the weight tile
@@ -95,9 +103,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             // ------------------------------------------------------------ TMA producer (both CTAs)
             if (lane == 0) {
                 uint32_t stage = 0, phase = 0;
-                for (int pt = pair; pt < pair_tiles; pt += num_pairs) {
-                    const int t = 2 * pt + static_cast<int>(rank);          // may be == total_tiles: all-zero tile
-                    const int img = t / tiles_img, rem = t - img * tiles_img;
+                for (int item = pair; item < num_items; item += num_pairs) {
+                  const int img = item / a.groups_img, p0 = (item - img * a.groups_img) * a.G, p1 = min(a.pt_img, p0 + a.G);
+                  for (int ptl = p0; ptl < p1; ++ptl) {
+                    const int rem = 2 * ptl + static_cast<int>(rank);       // tile inside the image; == tiles_img: a tile past the
+                                                                            // last one (odd tile count), computed but never stored
                     const int oy0 = (rem / a.tiles_x) * a.TH, ox0 = (rem % a.tiles_x) * a.TW;
                     const int n0 = static_cast<int>(rank) * (a.BN / 2);
                     int kb = 0;
@@ -118,6 +128,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             }
                         }
                     }
+                  }
                 }
             }
             __syncwarp();
@@ -129,7 +140,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const uint32_t idesc = umma_idesc_bf16(256, a.BN);
                 uint32_t stage = 0, phase = 0;
                 int it = 0;
-                for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++it) {
+                for (int item = pair; item < num_items; item += num_pairs) {
+                  const int g0 = (item % a.groups_img) * a.G, ntl = min(a.pt_img, g0 + a.G) - g0;
+                  for (int jt = 0; jt < ntl; ++jt, ++it) {
                     const uint32_t as = it & 1, aphase = (it >> 1) & 1;
                     mbar_wait(tempty0 + 8 * as, aphase ^ 1);
                     tc_fence_after();
@@ -153,6 +166,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         if (elected && kb == num_kb - 1) umma_commit_pair(tfull0 + 8 * as);
                         if (++stage == C_STAGES) { stage = 0; phase ^= 1; }
                     }
+                  }
                 }
             }
             __syncwarp();
@@ -164,41 +178,93 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int half = (warp - 4) >> 2;
         const int half_cols = a.BN / 2;                       // 32, 64 or 128 columns per epilogue half
         int it = 0;
-        for (int pt = pair; pt < pair_tiles; pt += num_pairs, ++it) {
-            const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-            const int t = 2 * pt + static_cast<int>(rank);
-            const int img = t / tiles_img, rem = t - img * tiles_img;
-            const int i = q * 32 + lane;                      // pixel index inside the tile
-            const int oy = (rem / a.tiles_x) * a.TH + i / a.TW, ox = (rem % a.tiles_x) * a.TW + i % a.TW;
-            const bool ok = t < total_tiles && oy < a.Ho && ox < a.Wo;
-            float* orow = a.out + ((static_cast<size_t>(img) * a.Ho + oy) * a.Wo + ox) * a.Cout;
-            mbar_wait(tfull0 + 8 * as, aphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + as * 256 + half * half_cols + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-            for (int c0 = 0; c0 < half_cols; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + c0, v);
-                tmem_ld_wait();
-                const int col = half * half_cols + c0;
-                if (ok && col < a.Cout) {
+        for (int item = pair; item < num_items; item += num_pairs) {
+            const int img = item / a.groups_img, grp = item - img * a.groups_img;
+            const int p0 = grp * a.G, p1 = min(a.pt_img, p0 + a.G);
+            float ssum[4] = {0.f, 0.f, 0.f, 0.f}, ssq[4] = {0.f, 0.f, 0.f, 0.f};     // lane j: channel chunk*32 + j of this warp's half
+            for (int ptl = p0; ptl < p1; ++ptl, ++it) {
+                const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+                const int rem = 2 * ptl + static_cast<int>(rank);
+                const int i = q * 32 + lane;                      // pixel index inside the tile
+                const int oy = (rem / a.tiles_x) * a.TH + i / a.TW, ox = (rem % a.tiles_x) * a.TW + i % a.TW;
+                const bool ok = rem < tiles_img && oy < a.Ho && ox < a.Wo;
+                float* orow = a.out + ((static_cast<size_t>(img) * a.Ho + oy) * a.Wo + ox) * a.Cout;
+                mbar_wait(tfull0 + 8 * as, aphase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + as * 256 + half * half_cols + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (col + j < a.Cout) {               // Cout is a multiple of 4
-                            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                                   __uint_as_float(v[j + 3]));
-                            if (a.bias) {
-                                const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col + j));
-                                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                for (int ci = 0; ci < 4; ++ci) {
+                    const int c0 = ci * 32;
+                    if (c0 < half_cols) {                         // warp-uniform
+                        uint32_t v[32];
+                        tmem_ld_32x32(taddr + c0, v);
+                        tmem_ld_wait();
+                        const int col = half * half_cols + c0;
+                        if (ok && col < a.Cout) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                if (col + j < a.Cout) {           // Cout is a multiple of 4
+                                    float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                                           __uint_as_float(v[j + 3]));
+                                    if (a.bias) {
+                                        const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col + j));
+                                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                                        v[j] = __float_as_uint(o.x); v[j + 1] = __float_as_uint(o.y);
+                                        v[j + 2] = __float_as_uint(o.z); v[j + 3] = __float_as_uint(o.w);
+                                    }
+                                    *reinterpret_cast<float4*>(orow + col + j) = o;
+                                }
                             }
-                            *reinterpret_cast<float4*>(orow + col + j) = o;
+                        }
+                        if (a.partial) {
+                            // transpose-reduce over the warp's 32 pixels (pixels outside the image contribute 0):
+                            // lane j ends with this tile's totals of channel col + j
+                            float s[32], sq[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float f = ok ? __uint_as_float(v[j]) : 0.f;
+                                s[j] = f; sq[j] = f * f;
+                            }
+#pragma unroll
+                            for (int w = 16; w >= 1; w >>= 1) {
+                                const bool up = lane & w;
+#pragma unroll
+                                for (int j = 0; j < w; ++j) {
+                                    const float send_s = up ? s[j] : s[j + w], keep_s = up ? s[j + w] : s[j];
+                                    const float send_q = up ? sq[j] : sq[j + w], keep_q = up ? sq[j + w] : sq[j];
+                                    s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
+                                    sq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
+                                }
+                            }
+                            ssum[ci] += s[0];
+                            ssq[ci] += sq[0];
+                        }
+                        __syncwarp();
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive_cluster(tempty0 + 8 * as, 0);
+            }
+            if (a.partial) {
+                float* mine = comb + (warp - 4) * 256;            // [chunk][sum 32 | squares 32]
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) { mine[ci * 64 + lane] = ssum[ci]; mine[ci * 64 + 32 + lane] = ssq[ci]; }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (q == 0) {                                      // warps 4 and 8: the four pixel quadrants in a fixed order
+                    const float* c4 = comb + (half * 4) * 256;
+                    float* p = a.partial + ((static_cast<size_t>(img) * a.groups_img + grp) * 2 + rank) * 2 * a.Cout;
+#pragma unroll
+                    for (int ci = 0; ci < 4; ++ci) {
+                        const int col = half * half_cols + ci * 32 + lane;
+                        if (ci * 32 < half_cols && col < a.Cout) {
+                            const float* e = c4 + ci * 64;
+                            p[col] = ((e[lane] + e[256 + lane]) + e[512 + lane]) + e[768 + lane];
+                            p[a.Cout + col] = ((e[32 + lane] + e[256 + 32 + lane]) + e[512 + 32 + lane]) + e[768 + 32 + lane];
                         }
                     }
                 }
-                __syncwarp();
+                asm volatile("bar.sync 1, 256;" ::: "memory");    // comb is rewritten by the next item
             }
-            tc_fence_before();
-            mbar_arrive_cluster(tempty0 + 8 * as, 0);
         }
     }
 
@@ -213,8 +279,22 @@ using namespace pips;
 
 // x_hi/x_lo: (N, H, W, Cp) bf16; w_hi/w_lo: (BN, R*S*Cp) bf16 with BN = Cout rounded up to 64/128/256 (zero rows);
 // out: (N, Ho, Wo, Cout) fp32.
+// tile shape and work-item grouping from the output geometry alone (the partial-statistics layout depends on it)
+static void conv_geometry(int Ho, int Wo, int sx, ConvArgs& a) {
+    // widest power-of-two tile row that does not exceed the output width (<= 128), the rest in rows
+    int tw = 128;
+    while (tw > 8 && tw > Wo) tw >>= 1;
+    if (sx == 2 && (tw - 1) * 2 + 1 > 256) tw = 64;
+    a.TW = tw; a.TH = 128 / tw;
+    a.tiles_x = (Wo + a.TW - 1) / a.TW; a.tiles_y = (Ho + a.TH - 1) / a.TH;
+    a.pt_img = (a.tiles_x * a.tiles_y + 1) / 2;               // pair tiles per image
+    a.G = (a.pt_img + 31) / 32;                               // at most 32 groups (64 partial rows) per image
+    a.groups_img = (a.pt_img + a.G - 1) / a.G;
+}
+
 static int conv_tc_impl(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp, const void* w_hi, const void* w_lo,
-                        int Cout, int R, int S, int sy, int sx, int py, int px, const float* bias, float* out, void* stream) {
+                        int Cout, int R, int S, int sy, int sx, int py, int px, const float* bias, float* out, float* partial,
+                        void* stream) {
     if (!x_hi || !x_lo || !w_hi || !w_lo || !out) return fail("pips_conv_tc: null pointer");
     if (N <= 0 || H <= 0 || W <= 0 || Cp <= 0 || (Cp % BK)) return fail("pips_conv_tc: Cp must be a positive multiple of 64");
     if (Cout <= 0 || Cout > 256 || (Cout % 4)) return fail("pips_conv_tc: Cout must be a multiple of 4, at most 256");
@@ -230,13 +310,8 @@ static int conv_tc_impl(const void* x_hi, const void* x_lo, int N, int H, int W,
         int st = static_cast<int>(C_RING_BYTES / stage);
         a.stages = st > C_MAX_STAGES ? C_MAX_STAGES : st;      // BN 256: 3 x 64 KB, 128: 4 x 48 KB, 64: 4 x 40 KB
     }
-    // widest power-of-two tile row that does not exceed the output width (<= 128), the rest in rows
-    int tw = 128;
-    while (tw > 8 && tw > Wo) tw >>= 1;
-    if (sx == 2 && (tw - 1) * 2 + 1 > 256) tw = 64;
-    a.TW = tw; a.TH = 128 / tw;
-    a.tiles_x = (Wo + a.TW - 1) / a.TW; a.tiles_y = (Ho + a.TH - 1) / a.TH;
-    a.bias = bias; a.out = out;
+    conv_geometry(Ho, Wo, sx, a);
+    a.bias = bias; a.out = out; a.partial = partial;
 
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     {
@@ -264,10 +339,9 @@ static int conv_tc_impl(const void* x_hi, const void* x_lo, int N, int H, int W,
         cudaError_t e = ensure_dyn_smem(conv_tc_kernel, attr, C_SMEM_BYTES);
         if (e != cudaSuccess) return fail_cuda("pips_conv_tc: smem attribute", e);
     }
-    const int total_tiles = N * a.tiles_x * a.tiles_y;
-    const int pair_tiles = (total_tiles + 1) / 2;
+    const int items = N * a.groups_img;
     const int max_pairs = sm_count() / 2;
-    const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
+    const int pairs = items < max_pairs ? items : max_pairs;
     cudaError_t e = launch_pdl(conv_tc_kernel, dim3(2 * pairs), dim3(C_THREADS), C_SMEM_BYTES, static_cast<cudaStream_t>(stream), ma_hi, ma_lo,
                                mw_hi, mw_lo, a);
     if (e == cudaSuccess) e = cudaGetLastError();
@@ -276,7 +350,7 @@ static int conv_tc_impl(const void* x_hi, const void* x_lo, int N, int H, int W,
 
 extern "C" int pips_conv_tc(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp, const void* w_hi, const void* w_lo,
                             int Cout, int R, int S, int stride, int pad, const float* bias, float* out, void* stream) {
-    return conv_tc_impl(x_hi, x_lo, N, H, W, Cp, w_hi, w_lo, Cout, R, S, stride, stride, pad, pad, bias, out, stream);
+    return conv_tc_impl(x_hi, x_lo, N, H, W, Cp, w_hi, w_lo, Cout, R, S, stride, stride, pad, pad, bias, out, nullptr, stream);
 }
 
 // Anisotropic form (separate row / column stride and padding): the 7x7 stem runs as a 7x1 convolution over the
@@ -284,5 +358,24 @@ extern "C" int pips_conv_tc(const void* x_hi, const void* x_lo, int N, int H, in
 extern "C" int pips_conv_tc_aniso(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp, const void* w_hi, const void* w_lo,
                                   int Cout, int R, int S, int stride_y, int stride_x, int pad_y, int pad_x, const float* bias,
                                   float* out, void* stream) {
-    return conv_tc_impl(x_hi, x_lo, N, H, W, Cp, w_hi, w_lo, Cout, R, S, stride_y, stride_x, pad_y, pad_x, bias, out, stream);
+    return conv_tc_impl(x_hi, x_lo, N, H, W, Cp, w_hi, w_lo, Cout, R, S, stride_y, stride_x, pad_y, pad_x, bias, out, nullptr, stream);
+}
+
+// Number of partial-statistics rows per image pips_conv_tc_stats writes for this geometry (0: invalid geometry).
+extern "C" int pips_conv_tc_chunks(int H, int W, int R, int S, int stride_y, int stride_x, int pad_y, int pad_x) {
+    if (H <= 0 || W <= 0 || R <= 0 || S <= 0 || stride_y <= 0 || stride_x <= 0) return 0;
+    const int Ho = (H + 2 * pad_y - R) / stride_y + 1, Wo = (W + 2 * pad_x - S) / stride_x + 1;
+    if (Ho <= 0 || Wo <= 0) return 0;
+    ConvArgs a;
+    conv_geometry(Ho, Wo, stride_x, a);
+    return a.groups_img * 2;
+}
+
+// pips_conv_tc_aniso that also accumulates the InstanceNorm partial statistics of its output in the epilogue:
+// partial (N, pips_conv_tc_chunks(...), 2, Cout) fp32 = per chunk (sum, sum of squares) per channel, for pips_inorm_finalize.
+extern "C" int pips_conv_tc_stats(const void* x_hi, const void* x_lo, int N, int H, int W, int Cp, const void* w_hi, const void* w_lo,
+                                  int Cout, int R, int S, int stride_y, int stride_x, int pad_y, int pad_x, const float* bias,
+                                  float* out, float* partial, void* stream) {
+    if (!partial) return fail("pips_conv_tc_stats: null partial buffer");
+    return conv_tc_impl(x_hi, x_lo, N, H, W, Cp, w_hi, w_lo, Cout, R, S, stride_y, stride_x, pad_y, pad_x, bias, out, partial, stream);
 }

@@ -159,7 +159,9 @@ class _Pair:
         self.lo = torch.empty(N, H, W, self.Cp, dtype=torch.bfloat16, device=device)
 
 
-def conv_tc(x: _Pair, conv: torch.nn.Conv2d, bias: bool = False) -> torch.Tensor:
+def conv_tc(x: _Pair, conv: torch.nn.Conv2d, bias: bool = False, stats: bool = False):
+    """-> output (N,Ho,Wo,Cout) fp32; with ``stats`` also the InstanceNorm statistics (N,2,Cout) of the output, from
+    partial sums the convolution's epilogue accumulates (no separate pass over the output)."""
     lib = L.load()
     N, H, W = x.shape
     cout, cin, R, S = conv.weight.shape
@@ -167,12 +169,22 @@ def conv_tc(x: _Pair, conv: torch.nn.Conv2d, bias: bool = False) -> torch.Tensor
     st, pad = conv.stride[0], conv.padding[0]
     Ho, Wo = (H + 2 * pad - R) // st + 1, (W + 2 * pad - S) // st + 1
     w_hi, w_lo = _packed_weight(conv)
-    out = torch.empty(N, Ho, Wo, cout, dtype=torch.float32, device=x.hi.device)
+    dev = x.hi.device
+    out = torch.empty(N, Ho, Wo, cout, dtype=torch.float32, device=dev)
     b = conv.bias.detach().float().contiguous() if bias and conv.bias is not None else None
-    L.check(lib.pips_conv_tc(L.ptr(x.hi), L.ptr(x.lo), N, H, W, x.Cp, L.ptr(w_hi), L.ptr(w_lo), cout, R, S, st, pad,
-                             L.ptr(b), L.ptr(out), _st()), "pips_conv_tc")
-    LAUNCHES[0] += 1
-    return out
+    if not stats:
+        L.check(lib.pips_conv_tc(L.ptr(x.hi), L.ptr(x.lo), N, H, W, x.Cp, L.ptr(w_hi), L.ptr(w_lo), cout, R, S, st, pad,
+                                 L.ptr(b), L.ptr(out), _st()), "pips_conv_tc")
+        LAUNCHES[0] += 1
+        return out
+    chunks = lib.pips_conv_tc_chunks(H, W, R, S, st, st, pad, pad)
+    partial = torch.empty(N, chunks, 2, cout, dtype=torch.float32, device=dev)
+    stt = torch.empty(N, 2, cout, dtype=torch.float32, device=dev)
+    L.check(lib.pips_conv_tc_stats(L.ptr(x.hi), L.ptr(x.lo), N, H, W, x.Cp, L.ptr(w_hi), L.ptr(w_lo), cout, R, S, st, st, pad, pad,
+                                   L.ptr(b), L.ptr(out), L.ptr(partial), _st()), "pips_conv_tc_stats")
+    L.check(lib.pips_inorm_finalize(L.ptr(partial), N, chunks, Ho * Wo, cout, L.ptr(stt), _st()), "pips_inorm_finalize")
+    LAUNCHES[0] += 2
+    return out, stt
 
 
 def conv_rows_ok(x: _Pair, conv: torch.nn.Conv2d) -> bool:
@@ -207,8 +219,10 @@ def _conv_stats(ops: _Ops, x: _Pair, conv: torch.nn.Conv2d):
     """Convolution feeding an InstanceNorm: (output, statistics)."""
     if conv_rows_ok(x, conv):
         return conv_rows(x, conv)
-    y = conv_tc(x, conv)
-    return y, ops.stats(y)
+    if os.environ.get("PIPS_B200_CONV_STATS", "1") == "0":      # separate statistics pass (round 1), for A/B
+        y = conv_tc(x, conv)
+        return y, ops.stats(y)
+    return conv_tc(x, conv, stats=True)
 
 
 def _apply_pair(ops: _Ops, y, stats, r=None, stats_r=None, relu_main=True, relu_out=False, plain=False):
@@ -295,10 +309,14 @@ def _fnet_tc(enc: Encoder, rgb: torch.Tensor) -> torch.Tensor:
             "pips_stem_pack")
     w_hi, w_lo = _packed_stem_weight(enc.conv1)
     y = torch.empty(N, Ho, Wo, 64, dtype=torch.float32, device=rgb.device)
-    L.check(lib.pips_conv_tc_aniso(L.ptr(unf.hi), L.ptr(unf.lo), N, Ho + 3, Wo, 64, L.ptr(w_hi), L.ptr(w_lo), 64, 4, 1, 1, 1, 0, 0,
-                                   None, L.ptr(y), _st()), "pips_conv_tc_aniso")
-    LAUNCHES[0] += 2                                   # stem_pack + stem conv
-    X, XP = _apply_pair(ops, y, ops.stats(y), relu_main=True, plain=True)
+    chunks = lib.pips_conv_tc_chunks(Ho + 3, Wo, 4, 1, 1, 1, 0, 0)
+    partial = torch.empty(N, chunks, 2, 64, dtype=torch.float32, device=rgb.device)
+    s_stem = torch.empty(N, 2, 64, dtype=torch.float32, device=rgb.device)
+    L.check(lib.pips_conv_tc_stats(L.ptr(unf.hi), L.ptr(unf.lo), N, Ho + 3, Wo, 64, L.ptr(w_hi), L.ptr(w_lo), 64, 4, 1, 1, 1, 0, 0,
+                                   None, L.ptr(y), L.ptr(partial), _st()), "pips_conv_tc_stats")
+    L.check(lib.pips_inorm_finalize(L.ptr(partial), N, chunks, Ho * Wo, 64, L.ptr(s_stem), _st()), "pips_inorm_finalize")
+    LAUNCHES[0] += 3                                   # stem_pack + stem conv + statistics finalize
+    X, XP = _apply_pair(ops, y, s_stem, relu_main=True, plain=True)
 
     ctot = 64 + 96 + 128 + 128
     cat = _Pair(N, H8, W8, ctot, x.device)
@@ -309,8 +327,8 @@ def _fnet_tc(enc: Encoder, rgb: torch.Tensor) -> torch.Tensor:
             _, AP = _apply_pair(ops, y1, s1, relu_main=True)
             y2, s2 = _conv_stats(ops, AP, blk.conv2)
             if blk.downsample is not None:
-                d = conv_tc(XP, blk.downsample[0])
-                X, XP = _apply_pair(ops, y2, s2, r=d, stats_r=ops.stats(d), relu_main=True, relu_out=True, plain=True)
+                d, sd = _conv_stats(ops, XP, blk.downsample[0])
+                X, XP = _apply_pair(ops, y2, s2, r=d, stats_r=sd, relu_main=True, relu_out=True, plain=True)
             else:
                 X, XP = _apply_pair(ops, y2, s2, r=X, relu_main=True, relu_out=True, plain=True)
         Ns, Hs, Ws, Cs = X.shape
@@ -319,8 +337,8 @@ def _fnet_tc(enc: Encoder, rgb: torch.Tensor) -> torch.Tensor:
         LAUNCHES[0] += 1
         c_off += Cs
 
-    y = conv_tc(cat, enc.conv2)
-    _, AP = _apply_pair(ops, y, ops.stats(y), relu_main=True)
+    y, sy = _conv_stats(ops, cat, enc.conv2)
+    _, AP = _apply_pair(ops, y, sy, relu_main=True)
     return conv_tc(AP, enc.conv3, bias=True)
 
 

@@ -368,7 +368,15 @@ def test_conv_tc(N, H, W, cin, cout, k, stride, pad, bias):
     pair.hi[..., :cin] = hi
     pair.lo[..., :cin] = (x - hi.float()).to(torch.bfloat16)
     out = conv_tc(pair, conv, bias=bias)
+    out2, st = conv_tc(pair, conv, bias=bias, stats=True)       # same kernel + InstanceNorm partial statistics in the epilogue
     torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+    mean = out.double().mean(dim=(1, 2))
+    rstd = 1.0 / torch.sqrt(out.double().var(dim=(1, 2), unbiased=False) + 1e-5)
+    e_mean = (st[:, 0].double() - mean).abs().max().item()
+    e_rstd = ((st[:, 1].double() - rstd) / rstd).abs().max().item()
+    print(f"conv_tc statistics: mean err {e_mean:.2e}, rstd rel err {e_rstd:.2e}")
+    assert e_mean < 1e-5 and e_rstd < 1e-5
     ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), conv.weight.double(),
                                      conv.bias.double() if bias else None, stride=stride, padding=pad).permute(0, 2, 3, 1).float()
     assert out.shape == ref.shape

@@ -356,6 +356,9 @@ def test_update_and_vis_head():
     (1, 12, 16, 416, 256, 3, 1, 1, False),    # head conv, K = 9 x 448
     (3, 12, 16, 256, 128, 1, 1, 0, True),     # final 1x1 with bias; odd number of tiles
     (1, 192, 256, 64, 64, 3, 1, 1, False),    # full-size layer1 map: many tiles per pair
+    (2, 45, 80, 64, 64, 3, 1, 1, False),      # 45 x 80: odd tile count per image (a tile past the last one), several groups
+    (5, 24, 32, 128, 128, 3, 1, 1, False),    # layer4-like: 3 pair tiles per image, odd image count
+    (3, 15, 24, 64, 96, 3, 2, 1, False),      # stride 2 onto an 8 x 12 map: a single, partly empty tile per image
 ])
 def test_conv_tc(N, H, W, cin, cout, k, stride, pad, bias):
     from pips_b200.encoder_fast import _Pair, conv_tc

@@ -11,7 +11,10 @@ Pinning: the reference has no golden vectors or unit tests of its own
 itself*: ``tests/golden/make_golden.py`` imports the unmodified reference from
 /root/reference, loads the state_dict produced by ``init_state_dict`` below with
 ``strict=True`` and records its outputs; ``tests/test_oracle_golden.py`` replays
-them against this file.
+them against this file.  Recorded configurations: five small inference cases, the
+demo size, a supervised / ``is_train`` call with its score maps, a chained track,
+BASELINE cfg 2 at full size, the cfg 4 shape (8 x 720 x 1280; the 256-particle chunk
+the reference can hold) and the real demo frames ``demo_images/000100-000107.jpg``.
 
 Every function cites the reference lines it restates (paths relative to the
 reference root).  Model state is a flat ``dict[str, Tensor]`` with exactly the
